@@ -1,0 +1,167 @@
+/*
+ * dqmc_b200.h -- C ABI of the B200-native DQMC sweep library (libdqmc_b200.so).
+ *
+ * The reference (carstenbauer/MonteCarlo.jl) is pure Julia and has no FFI for this path;
+ * the seam is Julia dispatch.  The entry points below are what a `ccall` from the
+ * Julia glue (julia/GPULocalSweep.jl) binds, one per reference
+ * interface it replaces.  All paths are relative to /root/reference.
+ *
+ * Conventions
+ *  - every call returns int32 status: 0 = ok, < 0 = error (text via dqmc_last_error);
+ *    no exceptions or callbacks cross the ABI (maps to Julia error()/ExitCode,
+ *    src/helpers.jl:17-22).
+ *  - the caller owns every host buffer; the library copies during the call and never
+ *    retains host pointers.  The library owns all device memory and its stream.
+ *  - matrices are dense column-major double with leading dimension N (Julia Matrix{Float64});
+ *    BlockDiagonal Green's functions are passed as N x N x n_flavors; batches of chains as
+ *    one more trailing dimension.  conf is Int8 N x M per chain (field.conf,
+ *    src/flavors/DQMC/fields.jl:363-368), values +-1, [site, slice].
+ *  - slice / range indices crossing the ABI are 1-based like the reference's.
+ *  - a context is not thread-safe; contexts are independent (one per GPU / process).
+ *    Calls are synchronous: results are complete when the call returns.
+ */
+#ifndef DQMC_B200_H
+#define DQMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DQMC_OK 0
+#define DQMC_ERR_INVALID (-1)
+#define DQMC_ERR_CUDA (-2)
+#define DQMC_ERR_UNSUPPORTED (-3)
+#define DQMC_ERR_NO_DEVICE (-4)
+
+#define DQMC_FIELD_DENSITY_HIRSCH 0   /* DensityHirschField,  fields.jl:363-395, 1 flavor block  */
+#define DQMC_FIELD_MAGNETIC_HIRSCH 1  /* MagneticHirschField, fields.jl:412-451, 2 flavor blocks */
+
+typedef struct dqmc_ctx dqmc_ctx;
+
+/* What `init!(mc, ::GPULocalSweep)` hands over: DQMCParameters (parameters.jl:33-49),
+ * the stack's ranges and hopping exponentials (stack.jl:154-158, 235-239) and the field's
+ * coupling (fields.jl:370-376, 419-425). */
+typedef struct dqmc_desc {
+    int32_t n_sites;                  /* N = length(lattice)                                    */
+    int32_t n_slices;                 /* M = parameters.slices                                  */
+    int32_t field_kind;               /* DQMC_FIELD_*  (n_flavors = 1 density / 2 magnetic)     */
+    int32_t n_chains;                 /* independent Markov chains batched in this context      */
+    int32_t n_ranges;                 /* C = length(stack.ranges)                               */
+    const int32_t* range_first;       /* [C] first(stack.ranges[i]), 1-based                    */
+    const int32_t* range_last;        /* [C] last(stack.ranges[i]), 1-based inclusive           */
+    double alpha;                     /* field.alpha                                            */
+    const double* hopping_exp_squared;     /* exp(-dtau T)    N x N  stack.hopping_matrix_exp_squared     */
+    const double* hopping_exp_inv_squared; /* exp(+dtau T)           stack.hopping_matrix_exp_inv_squared */
+    const double* hopping_exp;             /* exp(-dtau T/2)         stack.hopping_matrix_exp             */
+    const double* hopping_exp_inv;         /* exp(+dtau T/2)         stack.hopping_matrix_exp_inv         */
+    int32_t check_sign_problem;       /* parameters.check_sign_problem      (parameters.jl:38)  */
+    int32_t check_propagation_error;  /* parameters.check_propagation_error (parameters.jl:39)  */
+    uint64_t seed;                    /* key of the counter RNG (include/dqmc_rng.h)            */
+    int64_t chain_offset;             /* global index of chain 0 (multi-GPU sharding)           */
+    int32_t device;                   /* CUDA device ordinal                                    */
+    int32_t delay_block;              /* sites per delayed-update block, 0 = auto               */
+} dqmc_desc;
+
+/* MagnitudeStats (src/flavors/DQMC/statistics.jl:9-38) per chain. */
+typedef struct dqmc_stats {
+    int64_t neg_count;  double neg_sumlog10, neg_min, neg_max;     /* negative_probability  */
+    int64_t prop_count; double prop_sumlog10, prop_min, prop_max;  /* propagation_error     */
+} dqmc_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+/* DQMCStack + initialize_stack + init_hopping_matrices upload (stack.jl:1-74, 160-249). */
+int32_t dqmc_create(const dqmc_desc* desc, dqmc_ctx** out);
+int32_t dqmc_destroy(dqmc_ctx* ctx);
+/* message of the last failing call on this context (or of dqmc_create when ctx == NULL). */
+const char* dqmc_last_error(const dqmc_ctx* ctx);
+int32_t dqmc_device_count(void);
+
+/* ---- field configuration: mc.field.conf (fields.jl:363-368) -------------------------------- */
+int32_t dqmc_set_conf(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, const int8_t* conf);
+int32_t dqmc_get_conf(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, int8_t* conf);
+
+/* ---- stack ------------------------------------------------------------------------------- */
+/* reverse_build_stack + propagate (stack.jl:284-308, 605; DQMC.jl:178-179): afterwards
+ * current_slice = 1, direction = +1 and greens = G_eff(1). */
+int32_t dqmc_build_stack(dqmc_ctx* ctx);
+/* build_stack (stack.jl:257-281): current_slice = M + 1, direction = -1. */
+int32_t dqmc_forward_build_stack(dqmc_ctx* ctx);
+/* propagate (stack.jl:605-730), n times. */
+int32_t dqmc_propagate(dqmc_ctx* ctx, int32_t n);
+/* [current_slice, current_range, direction] */
+int32_t dqmc_get_state(const dqmc_ctx* ctx, int32_t* out3);
+
+/* ---- the sweep ----------------------------------------------------------------------------- */
+/* update(::LocalSweep, mc, model, field) = local_sweep (local_updates.jl:7-14, 82), nsweeps times.
+ * uniforms: NULL -> counter RNG (dqmc_rng.h); else host table [nsweeps][n_chains][2M][N] of the
+ * Metropolis uniforms.  accepted: [n_chains] accepted flips summed over the nsweeps. */
+int32_t dqmc_sweep(dqmc_ctx* ctx, int32_t nsweeps, const double* uniforms, int64_t* accepted);
+/* One sweep with optional teacher forcing and traces, each [n_chains][2M][N]:
+ * forced != NULL replays the given accept decisions; probs / decisions (may be NULL) receive
+ * p = exp(-dE_boson) * detratio (local_updates.jl:31) and the decision of every proposal. */
+int32_t dqmc_sweep_traced(dqmc_ctx* ctx, const double* uniforms, const uint8_t* forced,
+                          double* probs, uint8_t* decisions, int64_t* accepted);
+/* sweep_spatial at the current slice only (local_updates.jl:23-60); arrays [n_chains][N]. */
+int32_t dqmc_sweep_spatial(dqmc_ctx* ctx, const double* uniforms, const uint8_t* forced,
+                           double* probs, uint8_t* decisions, int64_t* accepted);
+int32_t dqmc_set_sweep_index(dqmc_ctx* ctx, int64_t sweep);
+
+/* ---- results ------------------------------------------------------------------------------- */
+/* mc.stack.greens (effective Green's function), N x N x n_flavors per chain. */
+int32_t dqmc_get_greens(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, double* G);
+int32_t dqmc_set_greens(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, const double* G);
+/* greens!(mc) = exp(+dtau T/2) G_eff exp(-dtau T/2) (greens.jl:94-125). */
+int32_t dqmc_get_measured_greens(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, double* G);
+/* calculate_greens(mc, slice) from scratch (stack.jl:525-583), all chains; invalidates Ul..Tr. */
+int32_t dqmc_calculate_greens_at(dqmc_ctx* ctx, int32_t slice, int32_t safe_mult, double* G);
+int32_t dqmc_get_stats(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, dqmc_stats* stats);
+/* which: 0 u_stack[slot], 1 d_stack[slot], 2 t_stack[slot], 3 Ul, 4 Dl, 5 Tl, 6 Ur, 7 Dr, 8 Tr
+ * (stack.jl:13-22); matrices N x N x n_flavors, vectors N x n_flavors; slot is 1-based. */
+int32_t dqmc_get_stack_array(dqmc_ctx* ctx, int32_t chain, int32_t which, int32_t slot, double* out);
+
+/* ---- observables ---------------------------------------------------------------------------- */
+/* Accumulate the measured Green's function of every chain into device accumulators
+ * {count, sum, sum of squares} (stands in for push!(LogBinner, G), measurements/generic.jl:586). */
+int32_t dqmc_accumulate_greens(dqmc_ctx* ctx);
+/* Device pointer / element count of the accumulator block [count | sum | sumsq] so that the host
+ * (torch.distributed / NCCL.jl) can all-reduce it in place over NVLink. */
+int32_t dqmc_observable_buffer(dqmc_ctx* ctx, void** device_ptr, int64_t* n_doubles);
+/* all-reduce (sum) of the accumulator block over an existing NCCL communicator (ncclComm_t);
+ * NCCL is resolved at run time (dlopen libnccl.so.2), the communicator stays owned by the caller. */
+int32_t dqmc_reduce_observables(dqmc_ctx* ctx, void* nccl_comm);
+/* copy out: count, then mean and variance-of-the-mean inputs (sum, sumsq), N x N x n_flavors each. */
+int32_t dqmc_get_observables(dqmc_ctx* ctx, double* count, double* sum, double* sumsq);
+
+/* ---- operator level: the reference's linalg "operator API", batched over host arrays ------- */
+/* vmul!(C, op(A), op(B)) (linalg/real.jl:7-15, 72-102) */
+int32_t dqmc_op_vmul(int32_t device, int32_t n, int32_t batch, int32_t transA, int32_t transB,
+                     const double* A, const double* B, double* C);
+/* udt_AVX_pivot!(U, D, T, pivot, temp, Val(apply_pivot)) (linalg/UDT.jl:216-334); X is not modified,
+ * pivot is 1-based on return. */
+int32_t dqmc_op_udt(int32_t device, int32_t n, int32_t batch, int32_t apply_pivot, const double* X,
+                    double* U, double* D, double* T, int64_t* pivot);
+/* rdivp!(A, T, O, pivot) (linalg/real.jl:198-226); pivot 1-based, A overwritten. */
+int32_t dqmc_op_rdivp(int32_t device, int32_t n, int32_t batch, double* A, const double* T,
+                      const int64_t* pivot);
+/* calculate_greens_AVX!(Ul, Dl, Tl, Ur, Dr, Tr, G) (stack.jl:442-496); inputs are not modified. */
+int32_t dqmc_op_calculate_greens(int32_t device, int32_t n, int32_t batch, const double* Ul,
+                                 const double* Dl, const double* Tl, const double* Ur,
+                                 const double* Dr, const double* Tr, double* G);
+/* multiply_*slice_matrix*! (stack.jl:319-367) on the context's conf; which: 0 left, 1 right,
+ * 2 inv_right, 3 inv_left, 4 daggered_left; X is N x N x n_flavors x n_chains, in place. */
+int32_t dqmc_op_multiply_slice_matrix(dqmc_ctx* ctx, int32_t which, int32_t slice, double* X);
+/* wrap_greens!(mc, X, curr_slice, direction) (stack.jl:594-603) on host matrices. */
+int32_t dqmc_op_wrap_greens(dqmc_ctx* ctx, int32_t curr_slice, int32_t direction, double* X);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+/* number of CUDA kernels this context has launched so far. */
+int64_t dqmc_kernel_launches(const dqmc_ctx* ctx);
+/* largest n_sites the UDT kernel supports in this build. */
+int32_t dqmc_max_sites(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQMC_B200_H */

@@ -1,0 +1,287 @@
+"""Thin numpy-facing wrapper of the C ABI (include/dqmc_b200.h).  One `Context` == one
+`dqmc_ctx`: a batch of independent Markov chains on one B200.  All array arguments are
+host numpy arrays in the reference's (Julia, column-major) layouts:
+
+    conf     int8   (N, M, B)        conf[site, slice, chain]
+    greens   float64 (N, N, nb, B)   G[:, :, flavor block, chain]
+
+Arrays are Fortran-ordered so that the memory is exactly what Julia would pass to `ccall`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+FIELD_DENSITY_HIRSCH = 0
+FIELD_MAGNETIC_HIRSCH = 1
+
+
+class DQMCError(RuntimeError):
+    pass
+
+
+def _dp(a):
+    return a.ctypes.data_as(_lib.dp)
+
+
+def _f64(a, shape=None):
+    a = np.array(a, dtype=np.float64, order="F", copy=True)
+    if shape is not None:
+        assert a.shape == tuple(shape), (a.shape, shape)
+    return a
+
+
+class Context:
+    def __init__(self, *, n_sites, n_slices, field_kind, n_chains, ranges, alpha,
+                 hopping_exp_squared, hopping_exp_inv_squared, hopping_exp, hopping_exp_inv,
+                 check_sign_problem=True, check_propagation_error=True, seed=1234, chain_offset=0,
+                 device=0, delay_block=0):
+        self._L = _lib.load()
+        self.N, self.M, self.kind, self.B = int(n_sites), int(n_slices), int(field_kind), int(n_chains)
+        self.nb = 1 if self.kind == FIELD_DENSITY_HIRSCH else 2
+        self.ranges = [(int(a), int(b)) for a, b in ranges]
+        self.C = len(self.ranges)
+        rf = np.array([r[0] for r in self.ranges], dtype=np.int32)
+        rl = np.array([r[1] for r in self.ranges], dtype=np.int32)
+        mats = [_f64(m, (self.N, self.N)) for m in
+                (hopping_exp_squared, hopping_exp_inv_squared, hopping_exp, hopping_exp_inv)]
+        d = _lib.Desc()
+        d.n_sites, d.n_slices, d.field_kind, d.n_chains, d.n_ranges = self.N, self.M, self.kind, self.B, self.C
+        d.range_first = rf.ctypes.data_as(_lib.i32p)
+        d.range_last = rl.ctypes.data_as(_lib.i32p)
+        d.alpha = float(alpha)
+        d.hopping_exp_squared, d.hopping_exp_inv_squared = _dp(mats[0]), _dp(mats[1])
+        d.hopping_exp, d.hopping_exp_inv = _dp(mats[2]), _dp(mats[3])
+        d.check_sign_problem, d.check_propagation_error = int(check_sign_problem), int(check_propagation_error)
+        d.seed, d.chain_offset, d.device, d.delay_block = int(seed), int(chain_offset), int(device), int(delay_block)
+        h = C.c_void_p()
+        rc = self._L.dqmc_create(C.byref(d), C.byref(h))
+        if rc != 0:
+            raise DQMCError(f"dqmc_create failed ({rc}): {self._L.dqmc_last_error(None).decode()}")
+        self._h = h
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise DQMCError(f"dqmc_b200 error {rc}: {self._L.dqmc_last_error(self._h).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dqmc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ field
+    def set_conf(self, conf, chain0=0):
+        conf = np.asfortranarray(conf, dtype=np.int8)
+        if conf.ndim == 2:
+            conf = conf.reshape(self.N, self.M, 1, order="F")
+        assert conf.shape[:2] == (self.N, self.M)
+        self._ck(self._L.dqmc_set_conf(self._h, chain0, conf.shape[2], conf.ctypes.data_as(_lib.i8p)))
+
+    def get_conf(self, chain0=0, nchains=None):
+        nchains = self.B - chain0 if nchains is None else nchains
+        out = np.zeros((self.N, self.M, nchains), dtype=np.int8, order="F")
+        self._ck(self._L.dqmc_get_conf(self._h, chain0, nchains, out.ctypes.data_as(_lib.i8p)))
+        return out
+
+    # ------------------------------------------------------------------ stack
+    def build_stack(self):
+        self._ck(self._L.dqmc_build_stack(self._h))
+
+    def forward_build_stack(self):
+        self._ck(self._L.dqmc_forward_build_stack(self._h))
+
+    def propagate(self, n=1):
+        self._ck(self._L.dqmc_propagate(self._h, int(n)))
+
+    @property
+    def state(self):
+        s = (C.c_int32 * 3)()
+        self._ck(self._L.dqmc_get_state(self._h, s))
+        return tuple(s)
+
+    # ------------------------------------------------------------------ sweeps
+    def sweep(self, nsweeps=1, uniforms=None):
+        """-> accepted flips per chain.  uniforms: (nsweeps, B, 2M, N) C-ordered table or None."""
+        acc = np.zeros(self.B, dtype=np.int64)
+        u = None
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+            assert uniforms.size == nsweeps * self.B * 2 * self.M * self.N
+            u = _dp(uniforms)
+        self._ck(self._L.dqmc_sweep(self._h, int(nsweeps), u, acc.ctypes.data_as(_lib.i64p)))
+        return acc
+
+    def sweep_traced(self, uniforms=None, forced=None):
+        """One sweep -> (accepted[B], probs[B, 2M, N], decisions[B, 2M, N])."""
+        shp = (self.B, 2 * self.M, self.N)
+        probs = np.zeros(shp)
+        dec = np.zeros(shp, dtype=np.uint8)
+        acc = np.zeros(self.B, dtype=np.int64)
+        u = f = None
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64); assert uniforms.shape == shp
+            u = _dp(uniforms)
+        if forced is not None:
+            forced = np.ascontiguousarray(forced, dtype=np.uint8); assert forced.shape == shp
+            f = forced.ctypes.data_as(_lib.u8p)
+        self._ck(self._L.dqmc_sweep_traced(self._h, u, f, _dp(probs), dec.ctypes.data_as(_lib.u8p),
+                                           acc.ctypes.data_as(_lib.i64p)))
+        return acc, probs, dec
+
+    def sweep_spatial(self, uniforms=None, forced=None):
+        shp = (self.B, self.N)
+        probs = np.zeros(shp)
+        dec = np.zeros(shp, dtype=np.uint8)
+        acc = np.zeros(self.B, dtype=np.int64)
+        u = f = None
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64); assert uniforms.shape == shp
+            u = _dp(uniforms)
+        if forced is not None:
+            forced = np.ascontiguousarray(forced, dtype=np.uint8); assert forced.shape == shp
+            f = forced.ctypes.data_as(_lib.u8p)
+        self._ck(self._L.dqmc_sweep_spatial(self._h, u, f, _dp(probs), dec.ctypes.data_as(_lib.u8p),
+                                            acc.ctypes.data_as(_lib.i64p)))
+        return acc, probs, dec
+
+    def set_sweep_index(self, s):
+        self._ck(self._L.dqmc_set_sweep_index(self._h, int(s)))
+
+    # ------------------------------------------------------------------ results
+    def _gshape(self, nchains):
+        return (self.N, self.N, self.nb, nchains)
+
+    def greens(self, chain0=0, nchains=None):
+        nchains = self.B - chain0 if nchains is None else nchains
+        out = np.zeros(self._gshape(nchains), order="F")
+        self._ck(self._L.dqmc_get_greens(self._h, chain0, nchains, _dp(out)))
+        return out
+
+    def set_greens(self, G, chain0=0):
+        G = _f64(G)
+        if G.ndim == 3:
+            G = G.reshape(self.N, self.N, self.nb, 1, order="F")
+        self._ck(self._L.dqmc_set_greens(self._h, chain0, G.shape[3], _dp(G)))
+
+    def measured_greens(self, chain0=0, nchains=None):
+        nchains = self.B - chain0 if nchains is None else nchains
+        out = np.zeros(self._gshape(nchains), order="F")
+        self._ck(self._L.dqmc_get_measured_greens(self._h, chain0, nchains, _dp(out)))
+        return out
+
+    def calculate_greens_at(self, slice_, safe_mult):
+        out = np.zeros(self._gshape(self.B), order="F")
+        self._ck(self._L.dqmc_calculate_greens_at(self._h, int(slice_), int(safe_mult), _dp(out)))
+        return out
+
+    def stats(self):
+        arr = (_lib.Stats * self.B)()
+        self._ck(self._L.dqmc_get_stats(self._h, 0, self.B, arr))
+        return [{k: getattr(s, k) for k, _ in _lib.Stats._fields_} for s in arr]
+
+    _WHICH = {"u_stack": 0, "d_stack": 1, "t_stack": 2, "Ul": 3, "Dl": 4, "Tl": 5, "Ur": 6, "Dr": 7, "Tr": 8}
+
+    def stack_array(self, which, slot=1, chain=0):
+        w = self._WHICH[which]
+        out = np.zeros((self.N, self.nb), order="F") if w in (1, 4, 7) else np.zeros((self.N, self.N, self.nb), order="F")
+        self._ck(self._L.dqmc_get_stack_array(self._h, int(chain), w, int(slot), _dp(out)))
+        return out
+
+    # ------------------------------------------------------------------ observables
+    def accumulate_greens(self):
+        self._ck(self._L.dqmc_accumulate_greens(self._h))
+
+    def observable_buffer(self):
+        p = C.c_void_p(); n = C.c_int64()
+        self._ck(self._L.dqmc_observable_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def observables(self):
+        cnt = np.zeros(1)
+        s = np.zeros((self.N, self.N, self.nb), order="F")
+        s2 = np.zeros((self.N, self.N, self.nb), order="F")
+        self._ck(self._L.dqmc_get_observables(self._h, _dp(cnt), _dp(s), _dp(s2)))
+        return float(cnt[0]), s, s2
+
+    # ------------------------------------------------------------------ operator level on the context
+    _SLICE_OPS = {"left": 0, "right": 1, "inv_right": 2, "inv_left": 3, "daggered_left": 4}
+
+    def multiply_slice_matrix(self, which, slice_, X):
+        X = _f64(X, self._gshape(self.B))
+        self._ck(self._L.dqmc_op_multiply_slice_matrix(self._h, self._SLICE_OPS[which], int(slice_), _dp(X)))
+        return X
+
+    def wrap_greens(self, X, curr_slice, direction):
+        X = _f64(X, self._gshape(self.B))
+        self._ck(self._L.dqmc_op_wrap_greens(self._h, int(curr_slice), int(direction), _dp(X)))
+        return X
+
+    def kernel_launches(self):
+        return int(self._L.dqmc_kernel_launches(self._h))
+
+
+# ---------------------------------------------------------------------- operator level, stateless
+def _op_err(rc):
+    if rc != 0:
+        raise DQMCError(f"dqmc_b200 op error {rc}: {_lib.load().dqmc_last_error(None).decode()}")
+
+
+def _batched(a):
+    a = np.array(a, dtype=np.float64, order="F", copy=True)
+    return a.reshape(a.shape[0], a.shape[1], 1, order="F") if a.ndim == 2 else a
+
+
+def vmul(A, B, transA=False, transB=False, device=0):
+    """vmul!(C, op(A), op(B)); A, B: (n, n) or (n, n, batch)."""
+    A3, B3 = _batched(A), _batched(B)
+    out = np.zeros_like(A3, order="F")
+    _op_err(_lib.load().dqmc_op_vmul(device, A3.shape[0], A3.shape[2], int(transA), int(transB), _dp(A3), _dp(B3), _dp(out)))
+    return out if np.ndim(A) == 3 else out[:, :, 0]
+
+
+def udt_AVX_pivot(X, apply_pivot=True, device=0):
+    """-> U, D, T, pivot (1-based int64) like udt_AVX_pivot!(U, D, T, pivot, temp, Val(apply_pivot))."""
+    X3 = _batched(X)
+    n, _, b = X3.shape
+    U = np.zeros_like(X3, order="F"); T = np.zeros_like(X3, order="F")
+    D = np.zeros((n, b), order="F"); piv = np.zeros((n, b), dtype=np.int64, order="F")
+    _op_err(_lib.load().dqmc_op_udt(device, n, b, int(apply_pivot), _dp(X3), _dp(U), _dp(D), _dp(T),
+                                     piv.ctypes.data_as(_lib.i64p)))
+    if np.ndim(X) == 2:
+        return U[:, :, 0], D[:, 0], T[:, :, 0], piv[:, 0]
+    return U, D, T, piv
+
+
+def rdivp(A, T, pivot, device=0):
+    A3, T3 = _batched(A), _batched(T)
+    n, _, b = A3.shape
+    piv = np.asfortranarray(np.array(pivot, dtype=np.int64).reshape(n, b, order="F"))
+    _op_err(_lib.load().dqmc_op_rdivp(device, n, b, _dp(A3), _dp(T3), piv.ctypes.data_as(_lib.i64p)))
+    return A3 if np.ndim(A) == 3 else A3[:, :, 0]
+
+
+def calculate_greens_AVX(Ul, Dl, Tl, Ur, Dr, Tr, device=0):
+    m = [_batched(x) for x in (Ul, Tl, Ur, Tr)]
+    n, _, b = m[0].shape
+    dl = np.asfortranarray(np.array(Dl, dtype=np.float64).reshape(n, b, order="F"))
+    dr = np.asfortranarray(np.array(Dr, dtype=np.float64).reshape(n, b, order="F"))
+    G = np.zeros_like(m[0], order="F")
+    _op_err(_lib.load().dqmc_op_calculate_greens(device, n, b, _dp(m[0]), _dp(dl), _dp(m[1]), _dp(m[2]), _dp(dr),
+                                                  _dp(m[3]), _dp(G)))
+    return G if np.ndim(Ul) == 3 else G[:, :, 0]

@@ -1,0 +1,112 @@
+// common.cuh -- shared declarations of the dqmc_b200 CUDA library (sm_100a only).
+//
+// Data layout in HBM: every per-chain matrix is stored as
+// `nmat = n_chains * n_flavors` independent n x n column-major FP64 matrices with
+// leading dimension ld = n rounded up to even (16-byte aligned columns for
+// cp.async), matrix m = chain * n_flavors + block at offset m * ld * n.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace dqmc {
+
+extern long long g_kernel_launches;   // kernels launched by this library (instrumentation)
+
+// A diagonal factor fused into a kernel.  `field` mode evaluates
+// interaction_matrix_exp! (reference src/flavors/DQMC/fields.jl:380-386, 429-438)
+// on the fly from the Int8 HS field: exp(+-alpha) chosen by the sign of conf.
+struct Scale {
+    int mode;            // 0 none, 1 vec[i], 2 1/vec[i], 3 field
+    const double* vec;   // mode 1/2: base pointer, matrix m uses vec + m * stride
+    long long stride;
+    const int8_t* conf;  // mode 3: conf + chain * cstride + i  (already offset to the slice)
+    long long cstride;
+    double ep, em;       // mode 3: value for conf > 0 / conf < 0 in flavor block 0
+    int nb;              // flavor blocks per chain (matrix m -> chain m / nb, block m % nb)
+    int flip;            // mode 3: swap ep/em in block 1 (MagneticHirschField)
+};
+
+__host__ __device__ inline Scale no_scale() { Scale s{}; s.mode = 0; s.nb = 1; return s; }
+
+__device__ __forceinline__ double scale_at(const Scale& s, int m, int i)
+{
+    if (s.mode == 1) return s.vec[(long long)m * s.stride + i];
+    if (s.mode == 2) return 1.0 / s.vec[(long long)m * s.stride + i];
+    const int chain = m / s.nb, blk = m - chain * s.nb;
+    const bool up = s.conf[(long long)chain * s.cstride + i] > 0;
+    const bool sw = (s.flip != 0) && (blk == 1);
+    return (up != sw) ? s.ep : s.em;
+}
+
+// C[m] = beta * C[m] + alpha * diag(rs) * op(A[m]) * diag(ks) * op(B[m]) * diag(cs) + diag(add_diag)
+struct GemmParams {
+    int M, N, K;
+    const double* A; int lda; long long strideA; int transA;   // strideA == 0 -> shared by all matrices
+    const double* B; int ldb; long long strideB; int transB;
+    double* C; int ldc; long long strideC;
+    double alpha, beta;
+    Scale rs, ks, cs;
+    const double* add_diag; long long add_stride;
+    int batch;
+};
+
+cudaError_t launch_gemm(const GemmParams& p, cudaStream_t st);
+
+// ---- UDT (column-pivoted Householder QR) ----------------------------------
+struct UdtParams {
+    int n, ld, batch;
+    const double* A; long long strideA;      // input (not modified)
+    Scale colscale;                          // fused vmul!(tmp, A, Diagonal(d)) on load
+    double* U; long long strideU;            // explicit Q
+    double* D; long long strideD;            // |diag R| (0 -> 1)
+    double* T; long long strideT;            // pivot_applied: D^-1 R P^T ; else clean upper-triangular D^-1 R (logical order)
+    int* pivot; long long stridePivot;       // logical column j came from input column pivot[j] (0-based)
+    int pivot_applied;
+    double* Vwork; long long strideV;        // n x ld scratch per matrix (Householder vectors)
+    double* tau; long long strideTau;        // n scratch per matrix
+};
+cudaError_t launch_udt(const UdtParams& p, cudaStream_t st);
+int udt_max_n();
+
+// ---- rdivp: A <- A[:, pivot] * inv(T), T clean upper triangular ------------
+struct RdivpParams {
+    int n, ld, batch;
+    double* A; long long strideA;
+    const double* T; long long strideT;
+    const int* pivot; long long stridePivot;
+    double* work; long long strideW;         // n x ld scratch per matrix
+};
+cudaError_t launch_rdivp(const RdivpParams& p, cudaStream_t st);
+
+// ---- local updates (sweep_spatial) -----------------------------------------
+struct UpdateParams {
+    int n, ld, nb, kind, n_chains;
+    double* G; long long strideG;            // per matrix
+    int8_t* conf_slice; long long cstride;   // conf + slice offset; chain stride
+    double alpha;
+    const double* uniforms; long long ustride; // table for this slice visit (per chain stride) or null
+    unsigned long long seed; long long sweep; int step; long long chain0;
+    int check_sign;
+    int* accepted;                           // per chain counters (accumulated)
+    double* stats;                           // per chain: [neg_count, neg_sumlog, neg_min, neg_max]
+    const unsigned char* forced;             // optional teacher-forced decisions for this slice visit
+    double* probs;                           // optional trace of p
+    unsigned char* decisions;                // optional trace of accept decisions
+    long long tstride;                       // per-chain stride of forced / probs / decisions
+    int kb;                                  // delay block size
+};
+cudaError_t launch_update(const UpdateParams& p, cudaStream_t st);
+int update_pick_kb(int n, int nb);
+
+// ---- small elementwise helpers ---------------------------------------------
+cudaError_t launch_set_identity(double* A, int n, int ld, long long stride, int batch, cudaStream_t st);
+cudaError_t launch_fill(double* v, double val, long long count, cudaStream_t st);
+cudaError_t launch_permute_cols(const double* A, double* O, const int* pivot, int n, int ld,
+                                long long stride, long long pstride, int batch, cudaStream_t st);
+// per chain: d = max |A - B| over the chain's nb matrices; if d > thresh accumulate MagnitudeStats
+cudaError_t launch_prop_error(const double* A, const double* B, int n, int ld, long long stride_chain,
+                              int nb, int n_chains, double thresh, double* stats, cudaStream_t st);
+cudaError_t launch_accumulate(const double* G, double* sum, double* sumsq, long long count, cudaStream_t st);
+
+}  // namespace dqmc

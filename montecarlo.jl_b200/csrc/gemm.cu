@@ -1,0 +1,225 @@
+// gemm.cu -- batched FP64 tensor-core GEMM with fused diagonal scalings.
+//
+// Replaces the reference's `vmul!` family (src/flavors/DQMC/linalg/real.jl:7-102)
+// and the slice-matrix products built from it (src/flavors/DQMC/stack.jl:319-367):
+//     C = beta*C + alpha * diag(rs) * op(A) * diag(ks) * op(B) * diag(cs) + diag(add)
+// for a batch of independent column-major matrices; A or B may be shared by the
+// whole batch (stride 0), which is how the hopping exponentials are applied.
+//
+// sm_100a: tcgen05.mma has no f64 kind, so FP64 tensor math is the warp-level
+// DMMA (PTX mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).  One DMMA is 256 FMA and the
+// SM retires 64 FP64 FMA/clk, so operand delivery is never the limit: tiles are
+// staged with a 3-stage cp.async (LDGSTS) ring into padded shared memory laid out
+// so that every fragment load is bank-conflict free (leading dimension = 4 mod 16
+// doubles).  Roofline: FP64 pipe.
+#include "common.cuh"
+
+namespace dqmc {
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+constexpr int BK = 16;
+constexpr int STAGES = 3;
+constexpr int KPAD = BK + 4;   // K-major tiles: (x, k) at x * KPAD + k ; 20 = 4 mod 16
+
+// Loads a tile of X (XT x BK in "x,k" terms) into shared memory.
+//  kmajor_global == false : global element (x, k) at g[x + k * ld]  (x contiguous) -> smem (x,k) at k*(XT+4) + x
+//  kmajor_global == true  : global element (x, k) at g[k + x * ld]  (k contiguous) -> smem (x,k) at x*KPAD + k
+template <int XT, bool KMAJOR, int NTHREADS>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int ld, int x0, int k0,
+                                          int X, int K, int tid)
+{
+    if constexpr (!KMAJOR) {
+        constexpr int CH = XT / 2;                 // 16-byte chunks per k-row
+        for (int c = tid; c < CH * BK; c += NTHREADS) {
+            const int k = c / CH, x = (c - k * CH) * 2;
+            const int gx = x0 + x, gk = k0 + k;
+            int bytes = 0;
+            if (gk < K) bytes = (gx + 1 < X) ? 16 : ((gx < X) ? 8 : 0);
+            const double* src = bytes ? (g + gx + (long long)gk * ld) : g;
+            cp_async16(s + k * (XT + 4) + x, src, bytes);
+        }
+    } else {
+        constexpr int CH = BK / 2;
+        for (int c = tid; c < CH * XT; c += NTHREADS) {
+            const int x = c / CH, k = (c - x * CH) * 2;
+            const int gx = x0 + x, gk = k0 + k;
+            int bytes = 0;
+            if (gx < X) bytes = (gk + 1 < K) ? 16 : ((gk < K) ? 8 : 0);
+            const double* src = bytes ? (g + gk + (long long)gx * ld) : g;
+            cp_async16(s + x * KPAD + k, src, bytes);
+        }
+    }
+}
+
+template <int XT, bool KMAJOR>
+__device__ __forceinline__ double tile_at(const double* s, int x, int k)
+{
+    if constexpr (!KMAJOR) return s[k * (XT + 4) + x];
+    else return s[x * KPAD + k];
+}
+
+template <int XT, bool KMAJOR> __host__ __device__ constexpr int tile_elems() { return KMAJOR ? XT * KPAD : BK * (XT + 4); }
+
+template <int BM, int BN, int WM, int WN, bool TA, bool TB>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+gemm_kernel(const GemmParams p)
+{
+    constexpr int NWM = BM / WM, NWN = BN / WN, NT = NWM * NWN * 32;
+    constexpr int MI = WM / 8, NJ = WN / 8;
+    // A tile is K-major in global iff transA (A stored K x M, k contiguous)
+    constexpr bool AK = TA;
+    // B tile (n, k): global B is K x N col-major (k contiguous) unless transB
+    constexpr bool BKM = !TB;
+    constexpr int AE = tile_elems<BM, AK>(), BE = tile_elems<BN, BKM>();
+
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * AE;
+    double* Ks = Bs + STAGES * BE;          // [STAGES][BK] inner scale
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp % NWM) * WM, wn0 = (warp / NWM) * WN;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, mat = blockIdx.z;
+
+    const double* A = p.A + (long long)mat * p.strideA;
+    const double* B = p.B + (long long)mat * p.strideB;
+    double* C = p.C + (long long)mat * p.strideC;
+    const bool has_ks = p.ks.mode != 0;
+
+    double acc[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int KT = (p.K + BK - 1) / BK;
+
+    auto issue = [&](int stage, int kt) {
+        const int k0 = kt * BK;
+        load_tile<BM, AK, NT>(As + stage * AE, A, p.lda, m0, k0, p.M, p.K, tid);
+        load_tile<BN, BKM, NT>(Bs + stage * BE, B, p.ldb, n0, k0, p.N, p.K, tid);
+        if (has_ks && tid < BK) {
+            const int gk = k0 + tid;
+            Ks[stage * BK + tid] = (gk < p.K) ? scale_at(p.ks, mat, gk) : 0.0;
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) issue(s, s);
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nxt = kt + STAGES - 1;
+        if (nxt < KT) issue(nxt % STAGES, nxt);
+        cp_async_commit();
+
+        const double* as = As + (kt % STAGES) * AE;
+        const double* bs = Bs + (kt % STAGES) * BE;
+        const double* ks = Ks + (kt % STAGES) * BK;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            const int k = kk * 4 + t;
+            double af[MI], bf[NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) af[i] = tile_at<BM, AK>(as, wm0 + i * 8 + g, k);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) bf[j] = tile_at<BN, BKM>(bs, wn0 + j * 8 + g, k);
+            if (has_ks) {
+                const double sk = ks[k];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) bf[j] *= sk;
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread owns C[row = g, cols = 2t, 2t+1] of every 8x8 tile
+    const bool has_rs = p.rs.mode != 0, has_cs = p.cs.mode != 0;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int row = m0 + wm0 + i * 8 + g;
+        if (row >= p.M) continue;
+        const double r = has_rs ? scale_at(p.rs, mat, row) : 1.0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = n0 + wn0 + j * 8 + 2 * t + e;
+                if (col >= p.N) continue;
+                double v = p.alpha * acc[i][j][e] * r;
+                if (has_cs) v *= scale_at(p.cs, mat, col);
+                if (p.add_diag && row == col) v += p.add_diag[(long long)mat * p.add_stride + row];
+                double* dst = C + row + (long long)col * p.ldc;
+                if (p.beta != 0.0) v += p.beta * (*dst);
+                *dst = v;
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int WM, int WN, bool TA, bool TB>
+static cudaError_t launch_cfg(const GemmParams& p, cudaStream_t st)
+{
+    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    constexpr int AE = tile_elems<BM, TA>(), BE = tile_elems<BN, !TB>();
+    constexpr int smem = (STAGES * (AE + BE) + STAGES * BK) * (int)sizeof(double);
+    auto kern = gemm_kernel<BM, BN, WM, WN, TA, TB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, p.batch);
+    kern<<<grid, NT, smem, st>>>(p);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+template <bool TA, bool TB>
+static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
+{
+    // pick the tile that wastes the least padded work; ties go to the larger tile
+    auto waste = [&](int bm, int bn) {
+        const double mm = (double)((p.M + bm - 1) / bm * bm), nn = (double)((p.N + bn - 1) / bn * bn);
+        return mm * nn / ((double)p.M * (double)p.N);
+    };
+    const double w64 = waste(64, 64), w48 = waste(48, 48), w32 = waste(32, 32);
+    if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) return launch_cfg<64, 64, 32, 32, TA, TB>(p, st);
+    if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
+    return launch_cfg<32, 32, 16, 16, TA, TB>(p, st);
+}
+
+cudaError_t launch_gemm(const GemmParams& p, cudaStream_t st)
+{
+    if (p.batch <= 0 || p.M <= 0 || p.N <= 0) return cudaSuccess;
+    if ((p.lda & 1) || (p.ldb & 1)) return cudaErrorInvalidValue;   // 16-byte cp.async columns
+    if (!p.transA && !p.transB) return launch_tiles<false, false>(p, st);
+    if (!p.transA && p.transB) return launch_tiles<false, true>(p, st);
+    if (p.transA && !p.transB) return launch_tiles<true, false>(p, st);
+    return launch_tiles<true, true>(p, st);
+}
+
+}  // namespace dqmc

@@ -1,0 +1,123 @@
+// misc.cu -- small elementwise / reduction kernels around the hot kernels.
+#include "common.cuh"
+#include <math.h>
+
+namespace dqmc {
+
+__global__ void set_identity_kernel(double* A, int n, int ld, long long stride)
+{
+    double* a = A + (long long)blockIdx.y * stride;
+    const long long tot = (long long)ld * n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % ld), j = (int)(e / ld);
+        a[e] = (i == j && i < n) ? 1.0 : 0.0;
+    }
+}
+
+cudaError_t launch_set_identity(double* A, int n, int ld, long long stride, int batch, cudaStream_t st)
+{
+    if (batch <= 0) return cudaSuccess;
+    const long long tot = (long long)ld * n;
+    dim3 grid((unsigned)((tot + 255) / 256 > 64 ? 64 : (tot + 255) / 256), (unsigned)batch);
+    set_identity_kernel<<<grid, 256, 0, st>>>(A, n, ld, stride);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+__global__ void fill_kernel(double* v, double val, long long count)
+{
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count;
+         e += (long long)gridDim.x * blockDim.x) v[e] = val;
+}
+
+cudaError_t launch_fill(double* v, double val, long long count, cudaStream_t st)
+{
+    if (count <= 0) return cudaSuccess;
+    long long b = (count + 255) / 256; if (b > 1184) b = 1184;
+    fill_kernel<<<(unsigned)b, 256, 0, st>>>(v, val, count);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+// O[:, j] = A[:, pivot[j]]   (first half of rdivp!, reference real.jl:204-209)
+__global__ void permute_cols_kernel(const double* A, double* O, const int* pivot, int n, int ld,
+                                    long long stride, long long pstride)
+{
+    const int mat = blockIdx.y;
+    const double* a = A + (long long)mat * stride;
+    double* o = O + (long long)mat * stride;
+    const int* pv = pivot + (long long)mat * pstride;
+    for (int j = blockIdx.x; j < n; j += gridDim.x) {
+        const int pj = pv[j];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) o[i + (long long)j * ld] = a[i + (long long)pj * ld];
+    }
+}
+
+cudaError_t launch_permute_cols(const double* A, double* O, const int* pivot, int n, int ld,
+                                long long stride, long long pstride, int batch, cudaStream_t st)
+{
+    if (batch <= 0) return cudaSuccess;
+    dim3 grid((unsigned)(n < 32 ? n : 32), (unsigned)batch);
+    permute_cols_kernel<<<grid, 128, 0, st>>>(A, O, pivot, n, ld, stride, pstride);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+// Propagation-error check (reference stack.jl:644-654, 699-709): d = max|A - B| over the
+// chain's matrices; if d > thresh push into MagnitudeStats [count, sum log10, min, max].
+__global__ void prop_error_kernel(const double* A, const double* B, int n, int ld, long long stride_chain,
+                                  int nb, double thresh, double* stats)
+{
+    const int chain = blockIdx.x;
+    const double* a = A + (long long)chain * stride_chain;
+    const double* b = B + (long long)chain * stride_chain;
+    double m = 0.0;
+    const long long tot = (long long)nb * ld * n;
+    for (long long e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int i = (int)(e % ld);
+        if (i < n) m = fmax(m, fabs(a[e] - b[e]));
+    }
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        if (m > thresh) {
+            double* s = stats + (long long)chain * 4;
+            s[0] += 1.0; s[1] += log10(m);
+            s[2] = fmin(s[2], m); s[3] = fmax(s[3], m);
+        }
+    }
+}
+
+cudaError_t launch_prop_error(const double* A, const double* B, int n, int ld, long long stride_chain,
+                              int nb, int n_chains, double thresh, double* stats, cudaStream_t st)
+{
+    if (n_chains <= 0) return cudaSuccess;
+    prop_error_kernel<<<(unsigned)n_chains, 256, 0, st>>>(A, B, n, ld, stride_chain, nb, thresh, stats);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+// per-element accumulators for the observable reduction: sum += x, sumsq += x^2
+__global__ void accumulate_kernel(const double* G, double* sum, double* sumsq, long long count)
+{
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count;
+         e += (long long)gridDim.x * blockDim.x) {
+        const double x = G[e];
+        sum[e] += x; sumsq[e] += x * x;
+    }
+}
+
+cudaError_t launch_accumulate(const double* G, double* sum, double* sumsq, long long count, cudaStream_t st)
+{
+    if (count <= 0) return cudaSuccess;
+    long long b = (count + 255) / 256; if (b > 1184) b = 1184;
+    accumulate_kernel<<<(unsigned)b, 256, 0, st>>>(G, sum, sumsq, count);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace dqmc

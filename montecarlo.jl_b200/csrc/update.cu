@@ -1,0 +1,246 @@
+// update.cu -- the local Hubbard-Stratonovich flip sweep over one time slice.
+//
+// Replaces `sweep_spatial` (reference src/flavors/DQMC/updates/local_updates.jl:23-60)
+// with `propose_local` / `calculate_detratio!` (fields.jl:388-393, 440-449, 63-84) and
+// `accept_local!` -> `update_greens!` (fields.jl:340-344, 271-286; linalg/updates.jl).
+//
+// The reference applies every accepted flip as an immediate rank-1 update
+//     G <- G - (I - G)[:, i] * (Delta / R) * G[i, :]
+// which is 16 n^2 bytes of memory traffic per accept.  Here one CTA owns one Markov
+// chain (all its flavor blocks) and works through the sites in blocks of `kb`:
+// the kb columns and rows of G that the block can touch are staged in shared
+// memory, accepted flips are kept as delayed factors (u_a, w_a) that overwrite the
+// staged columns/rows in place (compacted: the a-th accept goes to slot a <= j), the
+// current diagonal element / column / row are reconstructed on the fly
+//     G_cur[x, y] = G0[x, y] - sum_a u_a[x] w_a[y]
+// and at the end of the block G is updated once with a rank-k DMMA GEMM
+// (G -= U W).  Acceptance ratios are computed by warp 0 with a shuffle reduction.
+// The arithmetic per accepted flip is identical to the reference's up to the
+// association of the delayed sum.  Roofline: latency-bound proposals + an
+// HBM/FP64-balanced flush (2 n^2 k flops over 16 n^2 bytes), see DESIGN.md.
+#include "common.cuh"
+#include "../../include/dqmc_rng.h"
+#include <math.h>
+
+namespace dqmc {
+
+__device__ __forceinline__ void dmma884u(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+static inline int update_ldu(int n) { return n + (((4 - n) % 16) + 16) % 16; }   // == 4 mod 16
+
+int update_pick_kb(int n, int nb)
+{
+    const long long per_slot = (long long)nb * 2 * update_ldu(n) * 8;
+    long long kb = (200LL * 1024) / per_slot;
+    if (kb > 32) kb = 32;
+    kb &= ~3LL;
+    if (kb < 4) kb = 4;
+    if (kb > n) kb = (n + 3) & ~3;
+    return (int)kb;
+}
+
+struct UpdShared {
+    int dec[2];
+    double coef[2][2];
+};
+
+__global__ void update_kernel(const UpdateParams p, const int ldu, const double em2a, const double ep2a)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int n = p.n, nb = p.nb, kb = p.kb, ld = p.ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
+    const int chain = blockIdx.x;
+
+    double* Uc = sm;                                   // [nb][kb][ldu]   columns of G0 -> u_a
+    double* Wr = Uc + (size_t)nb * kb * ldu;           // [nb][kb][ldu]   rows of G0    -> w_a
+    UpdShared* sh = (UpdShared*)(Wr + (size_t)nb * kb * ldu);
+    int8_t* sconf = (int8_t*)(sh + 1);                 // [n]
+
+    double* G = p.G + (long long)chain * nb * p.strideG;
+    int8_t* conf = p.conf_slice + (long long)chain * p.cstride;
+    const double* utab = p.uniforms ? p.uniforms + (long long)chain * p.ustride : nullptr;
+    const unsigned char* forced = p.forced ? p.forced + (long long)chain * p.tstride : nullptr;
+
+    for (int i = tid; i < n; i += NT) sconf[i] = conf[i];
+
+    int accepted = 0;                  // tracked by every thread identically
+    double neg_cnt = 0.0, neg_sum = 0.0, neg_min = INFINITY, neg_max = -INFINITY;   // lane 0 of warp 0
+
+    for (int i0 = 0; i0 < n; i0 += kb) {
+        const int kbc = (n - i0 < kb) ? (n - i0) : kb;
+        __syncthreads();               // previous flush (global G) and sconf visible
+        // ---- stage the kbc columns and rows of G ---------------------------------
+        for (int b = 0; b < nb; ++b) {
+            const double* Gb = G + (long long)b * p.strideG;
+            double* ub = Uc + (size_t)b * kb * ldu;
+            double* wb = Wr + (size_t)b * kb * ldu;
+            for (int e = tid; e < kbc * n; e += NT) {
+                const int j = e / n, r = e - j * n;
+                ub[(size_t)j * ldu + r] = Gb[r + (long long)(i0 + j) * ld];
+            }
+            for (int e = tid; e < kbc * n; e += NT) {
+                const int c = e / kbc, j = e - c * kbc;
+                wb[(size_t)j * ldu + c] = Gb[(i0 + j) + (long long)c * ld];
+            }
+        }
+        __syncthreads();
+
+        int k = 0;                     // accepted flips in this block (delayed factors in slots 0..k-1)
+        for (int j = 0; j < kbc; ++j) {
+            const int i = i0 + j;
+            // ---- decision: warp 0 ---------------------------------------------------
+            if (warp == 0) {
+                const double x = (double)sconf[i];
+                // dE = -2 alpha x ; exp(dE) = x > 0 ? exp(-2a) : exp(+2a)
+                const double e_dE = (x > 0.0) ? em2a : ep2a;
+                const double e_mdE = (x > 0.0) ? ep2a : em2a;
+                double Rv[2], Dl[2];
+                for (int b = 0; b < nb; ++b) {
+                    const double* ub = Uc + (size_t)b * kb * ldu;
+                    const double* wb = Wr + (size_t)b * kb * ldu;
+                    double part = (lane < k) ? ub[(size_t)lane * ldu + i] * wb[(size_t)lane * ldu + i] : 0.0;
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    const double gii = ub[(size_t)j * ldu + i] - part;
+                    Dl[b] = ((p.kind == 1 && b == 1) ? e_mdE : e_dE) - 1.0;
+                    Rv[b] = 1.0 + Dl[b] * (1.0 - gii);
+                }
+                double prob;
+                if (p.kind == 0) prob = e_mdE * ((nb == 1) ? Rv[0] * Rv[0] : Rv[0] * Rv[1]);
+                else prob = Rv[0] * Rv[1];
+                if (lane == 0) {
+                    if (p.check_sign && prob < 0.0) {
+                        neg_cnt += 1.0; neg_sum += log10(fabs(prob));
+                        neg_min = fmin(neg_min, prob); neg_max = fmax(neg_max, prob);
+                    }
+                    int acc;
+                    if (forced) acc = forced[i] != 0;
+                    else if (prob > 1.0) acc = 1;
+                    else {
+                        const double u = utab ? utab[i]
+                                              : dqmc_uniform(p.seed, (uint64_t)(p.chain0 + chain),
+                                                             (uint64_t)p.sweep, (uint32_t)p.step, (uint32_t)i);
+                        acc = u < prob;
+                    }
+                    if (p.probs) p.probs[(long long)chain * p.tstride + i] = prob;
+                    if (p.decisions) p.decisions[(long long)chain * p.tstride + i] = (unsigned char)acc;
+                    sh->dec[j & 1] = acc;
+                    for (int b = 0; b < nb; ++b) sh->coef[j & 1][b] = Dl[b] / Rv[b];
+                    if (acc) { sconf[i] = (int8_t)(-sconf[i]); conf[i] = sconf[i]; }
+                }
+            }
+            __syncthreads();
+            const int acc = sh->dec[j & 1];
+            if (acc) {
+                // ---- new delayed factors (fields.jl:271-286) ------------------------------
+                for (int b = 0; b < nb; ++b) {
+                    double* ub = Uc + (size_t)b * kb * ldu;
+                    double* wb = Wr + (size_t)b * kb * ldu;
+                    const double coef = sh->coef[j & 1][b];
+                    for (int r = tid; r < n; r += NT) {
+                        double col = ub[(size_t)j * ldu + r];
+                        double row = wb[(size_t)j * ldu + r];
+                        for (int a = 0; a < k; ++a) {
+                            col -= ub[(size_t)a * ldu + r] * wb[(size_t)a * ldu + i];
+                            row -= ub[(size_t)a * ldu + i] * wb[(size_t)a * ldu + r];
+                        }
+                        // element (slot k, r) is only ever touched by this thread until the barrier
+                        ub[(size_t)k * ldu + r] = ((r == i) ? 1.0 : 0.0) - col;
+                        wb[(size_t)k * ldu + r] = coef * row;
+                    }
+                }
+                // the loop above reads slot-a entries at index i written by other threads in
+                // earlier steps (already separated by barriers) and slot j/k entries of its own r.
+                // BUT when k < j another thread's read of ub[k][i] (a < k only) never hits slot k. ok
+                ++k; ++accepted;
+                __syncthreads();
+            }
+        }
+
+        // ---- flush: G_b -= sum_{a<k} u_a w_a^T  (rank-k DMMA update) ---------------------
+        if (k > 0) {
+            const int g = lane >> 2, t = lane & 3;
+            const int tiles = (n + 31) / 32;
+            const int k4 = (k + 3) / 4;
+            for (int b = 0; b < nb; ++b) {
+                double* Gb = G + (long long)b * p.strideG;
+                const double* ub = Uc + (size_t)b * kb * ldu;
+                const double* wb = Wr + (size_t)b * kb * ldu;
+                for (int tile = warp; tile < tiles * tiles; tile += nwarps) {
+                    const int tm = (tile % tiles) * 32, tn = (tile / tiles) * 32;
+                    double acc2[4][4][2];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int nj = 0; nj < 4; ++nj) acc2[mi][nj][0] = acc2[mi][nj][1] = 0.0;
+                    for (int kk = 0; kk < k4; ++kk) {
+                        const int a = kk * 4 + t;
+                        const bool live = a < k;
+                        double af[4], bf[4];
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi) {
+                            const int r = tm + mi * 8 + g;
+                            af[mi] = (live && r < n) ? ub[(size_t)a * ldu + r] : 0.0;
+                        }
+#pragma unroll
+                        for (int nj = 0; nj < 4; ++nj) {
+                            const int c = tn + nj * 8 + g;
+                            bf[nj] = (live && c < n) ? wb[(size_t)a * ldu + c] : 0.0;
+                        }
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                            for (int nj = 0; nj < 4; ++nj)
+                                dmma884u(acc2[mi][nj][0], acc2[mi][nj][1], af[mi], bf[nj]);
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const int r = tm + mi * 8 + g;
+                        if (r >= n) continue;
+#pragma unroll
+                        for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = tn + nj * 8 + 2 * t + e;
+                                if (c < n) Gb[r + (long long)c * ld] -= acc2[mi][nj][e];
+                            }
+                    }
+                }
+            }
+        }
+    }
+
+    if (tid == 0) {
+        if (p.accepted) p.accepted[chain] += accepted;
+        if (p.stats && neg_cnt > 0.0) {
+            double* s = p.stats + (long long)chain * 4;
+            s[0] += neg_cnt; s[1] += neg_sum; s[2] = fmin(s[2], neg_min); s[3] = fmax(s[3], neg_max);
+        }
+    }
+}
+
+cudaError_t launch_update(const UpdateParams& p, cudaStream_t st)
+{
+    if (p.n_chains <= 0) return cudaSuccess;
+    const int ldu = update_ldu(p.n);
+    int nt = ((p.n + 31) / 32) * 32;
+    if (nt < 64) nt = 64;
+    if (nt > 1024) nt = 1024;
+    const size_t smem = (size_t)p.nb * 2 * p.kb * ldu * sizeof(double) + sizeof(UpdShared) + (size_t)p.n + 16;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const double em2a = exp(-2.0 * p.alpha), ep2a = exp(2.0 * p.alpha);
+    update_kernel<<<(unsigned)p.n_chains, nt, smem, st>>>(p, ldu, em2a, ep2a);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace dqmc

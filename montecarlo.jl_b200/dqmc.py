@@ -1,0 +1,252 @@
+"""DQMC(model; beta, delta_tau, safe_mult, ...), run!, greens, measurements -- the user-facing
+API of the reference for this path, served by the CUDA library.
+
+Mirrors src/flavors/DQMC/DQMC.jl:32-64 (constructor), :144-191 (init!), :200-225 (sweep_once!),
+:252-394 (run!), parameters.jl:84-139, fields.jl:363-451, greens.jl:94-125 and the
+`mc[:G] = greens_measurement(mc, model)` sugar (Measurements.jl:318-323).  Julia's `run!` is
+`run_b`/`run` here (no `!` in Python identifiers).  One DQMC object drives `n_chains`
+independent Markov chains of the same model and parameters (the reference would use a
+Vector{DQMC}); chain 0 is what `mc.field.conf` / `mc.stack.greens` show by default.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+
+from .context import FIELD_DENSITY_HIRSCH, FIELD_MAGNETIC_HIRSCH, Context
+from .models import HubbardModel, choose_field, hopping_matrix
+
+
+def _julia_round(x: float) -> int:
+    return int(round(x))          # round-half-even, like Julia's round(Int, x)
+
+
+class DQMCParameters:
+    """parameters.jl:33-139 (same keyword semantics, same slice arithmetic)."""
+
+    def __init__(self, *, thermalization=100, sweeps=100, silent=False, check_sign_problem=True,
+                 check_propagation_error=True, safe_mult=10, measure_rate=10, print_rate=None,
+                 checkerboard=False, beta=None, delta_tau=None, slices=None):
+        given = {k for k, v in (("beta", beta), ("delta_tau", delta_tau), ("slices", slices)) if v is not None}
+        if given == {"beta"}:
+            delta_tau = 0.1
+            given = {"beta", "delta_tau"}
+        if len(given) < 2:
+            raise ValueError(f"Invalid keyword arguments to DQMCParameters: {sorted(given)}")
+        if given == {"beta", "delta_tau", "slices"}:
+            s = _julia_round(beta / delta_tau)
+            if s != slices:
+                raise ValueError(f"Given slices ({slices}) does not match calculated slices beta/delta_tau ~ {s}")
+        elif given == {"beta", "slices"}:
+            delta_tau = beta / slices
+        elif given == {"delta_tau", "slices"}:
+            beta = delta_tau * slices
+        else:
+            slices = _julia_round(beta / delta_tau)
+        if checkerboard:
+            raise NotImplementedError("checkerboard decomposition is outside the B200 sweep path (SURVEY 2, row 19)")
+        self.thermalization, self.sweeps, self.silent = int(thermalization), int(sweeps), bool(silent)
+        self.check_sign_problem, self.check_propagation_error = bool(check_sign_problem), bool(check_propagation_error)
+        self.safe_mult, self.measure_rate = int(safe_mult), int(measure_rate)
+        self.print_rate = max(10, (self.thermalization + self.sweeps) // 100) if print_rate is None else int(print_rate)
+        self.beta, self.delta_tau, self.slices = float(beta), float(delta_tau), int(slices)
+        self.checkerboard = False
+
+
+def generate_chunks(length: int, max_chunk_size: int):
+    """stack.jl:154-158 -> [(first, last)] 1-based inclusive."""
+    n_chunks = -(-length // max_chunk_size)
+    step = length / n_chunks
+    return [(_julia_round((i - 1) * step) + 1, _julia_round(i * step)) for i in range(1, n_chunks + 1)]
+
+
+def sym_exp(A: np.ndarray) -> np.ndarray:
+    """exp of a Hermitian matrix through its eigen-decomposition (stack.jl:235-239 -> fallback_exp)."""
+    w, V = np.linalg.eigh(0.5 * (A + A.T))
+    return np.asfortranarray((V * np.exp(w)) @ V.T)
+
+
+class HirschField:
+    """DensityHirschField / MagneticHirschField (fields.jl:363-451): alpha and the Int8 conf."""
+
+    def __init__(self, name: str, param: DQMCParameters, model: HubbardModel, n_chains: int):
+        self.name = name
+        if name == "DensityHirschField":
+            self.kind = FIELD_DENSITY_HIRSCH
+            self.alpha = math.acosh(math.exp(0.5 * param.delta_tau * model.U))     # fields.jl:372
+        elif name == "MagneticHirschField":
+            self.kind = FIELD_MAGNETIC_HIRSCH
+            self.alpha = math.acosh(math.exp(-0.5 * param.delta_tau * model.U))    # fields.jl:421
+        else:
+            raise NotImplementedError(f"{name}: only the real Hirsch fields are on the B200 path (SURVEY 2, row 3)")
+        self.confs = np.ones((len(model.l), param.slices, n_chains), dtype=np.int8, order="F")
+
+    @property
+    def conf(self):
+        return self.confs[:, :, 0]
+
+    def rand(self, rng: np.random.Generator):
+        """rand!(field) (fields.jl:330): iid +-1."""
+        self.confs[...] = rng.choice(np.array([-1, 1], dtype=np.int8), size=self.confs.shape)
+
+    def compress(self, chain=0):
+        """BitArray(conf .== 1) (fields.jl:331)."""
+        return np.packbits(self.confs[:, :, chain].ravel(order="F") == 1)
+
+    def decompress(self, bits, chain=0):
+        n = self.confs.shape[0] * self.confs.shape[1]
+        c = np.unpackbits(bits)[:n].astype(np.int8) * 2 - 1
+        self.confs[:, :, chain] = c.reshape(self.confs.shape[:2], order="F")
+
+
+class _StackView:
+    """Read-only window on the device-resident DQMCStack of chain 0 (stack.jl:1-74)."""
+
+    def __init__(self, mc):
+        self._mc = mc
+
+    @property
+    def greens(self):
+        g = self._mc.ctx.greens(0, 1)[:, :, :, 0]
+        return g[:, :, 0] if self._mc.ctx.nb == 1 else g
+
+    @property
+    def current_slice(self):
+        return self._mc.ctx.state[0]
+
+    @property
+    def direction(self):
+        return self._mc.ctx.state[2]
+
+    @property
+    def ranges(self):
+        return [range(a, b + 1) for a, b in self._mc.ctx.ranges]
+
+
+class GreensMeasurement:
+    """greens_measurement(mc, model) (measurements/constructors/greens.jl:17-40) with a plain
+    {count, sum, sum of squares} accumulator per chain standing in for BinningAnalysis' LogBinner
+    (third-party, arithmetic unpinned -- SURVEY 8c)."""
+
+    def __init__(self, mc):
+        nb = mc.ctx.nb
+        self.count = 0
+        self.sum = np.zeros((mc.ctx.N, mc.ctx.N, nb, mc.ctx.B), order="F")
+        self.sumsq = np.zeros_like(self.sum)
+
+    def push(self, G):
+        self.count += 1
+        self.sum += G
+        self.sumsq += G * G
+
+    def mean(self, chain=None):
+        m = self.sum / max(self.count, 1)
+        m = m.mean(axis=3) if chain is None else m[:, :, :, chain]
+        return m[:, :, 0] if m.shape[2] == 1 else m
+
+    def std_error(self):
+        n = self.count * self.sum.shape[3]
+        mean = self.sum.sum(axis=3) / n
+        var = np.maximum(self.sumsq.sum(axis=3) / n - mean ** 2, 0.0)
+        return np.sqrt(var / max(n - 1, 1))
+
+
+def greens_measurement(mc, model=None):
+    return GreensMeasurement(mc)
+
+
+class DQMC:
+    """DQMC(model; beta, delta_tau, safe_mult, thermalization, sweeps, measure_rate, seed, field, ...)."""
+
+    def __init__(self, model: HubbardModel, *, seed=-1, field=None, n_chains=1, device=0, chain_offset=0,
+                 delay_block=0, **kwargs):
+        self.model = model
+        self.parameters = DQMCParameters(**kwargs)
+        self._rng = np.random.default_rng(None if seed == -1 else seed)
+        self.field = HirschField(field or choose_field(model), self.parameters, model, n_chains)
+        self.field.rand(self._rng)                                  # DQMC.jl:50
+        self.measurements = {}
+        self.thermalization_measurements = {}
+        self.last_sweep = 0
+        self.accepted = np.zeros(n_chains, dtype=np.int64)
+        self.total = 0
+        # init_hopping_matrices (stack.jl:209-249)
+        T = hopping_matrix(model)
+        if not np.allclose(T, T.T):
+            raise ValueError("The hopping matrix is not approximately Hermitian (stack.jl:213-224)")
+        dt = self.parameters.delta_tau
+        self.hopping_matrix = T
+        self.ctx = Context(
+            n_sites=len(model.l), n_slices=self.parameters.slices, field_kind=self.field.kind, n_chains=n_chains,
+            ranges=generate_chunks(self.parameters.slices, self.parameters.safe_mult), alpha=self.field.alpha,
+            hopping_exp_squared=sym_exp(-dt * T), hopping_exp_inv_squared=sym_exp(dt * T),
+            hopping_exp=sym_exp(-0.5 * dt * T), hopping_exp_inv=sym_exp(0.5 * dt * T),
+            check_sign_problem=self.parameters.check_sign_problem,
+            check_propagation_error=self.parameters.check_propagation_error,
+            seed=(1234 if seed == -1 else seed), chain_offset=chain_offset, device=device, delay_block=delay_block)
+        self.stack = _StackView(self)
+        self._initialized = False
+
+    # mc[:G] = greens_measurement(mc, model)   (Measurements.jl:318-323)
+    def __setitem__(self, key, m):
+        self.measurements[key] = m
+
+    def __getitem__(self, key):
+        return self.measurements[key]
+
+    def init(self):
+        """init!(mc) + the stack part of initialize_run (DQMC.jl:144-191)."""
+        self.ctx.set_conf(self.field.confs)
+        self.ctx.build_stack()
+        self._initialized = True
+
+    def sweep_once(self, uniforms=None):
+        """sweep_once! (DQMC.jl:200-225) without the measurement hand-off."""
+        acc = self.ctx.sweep(1, uniforms)
+        self.accepted += acc
+        self.total += 2 * self.ctx.N * self.ctx.M
+        self.last_sweep += 1
+        return acc / (2 * self.ctx.N * self.ctx.M)
+
+    def greens(self, chain=None):
+        """greens(mc) (greens.jl:94-125): exp(+dtau T / 2) G_eff exp(-dtau T / 2)."""
+        g = self.ctx.measured_greens()
+        g = g[:, :, :, 0] if chain is None else g[:, :, :, chain]
+        return g[:, :, 0] if self.ctx.nb == 1 else g
+
+    def sync_field(self):
+        self.field.confs[...] = self.ctx.get_conf()
+
+    def analysis(self):
+        """DQMCAnalysis (statistics.jl:40-50) per chain."""
+        return self.ctx.stats()
+
+
+def run(mc: DQMC, *, verbose=False, min_update_rate=0.001):
+    """run!(mc) (DQMC.jl:252-394): thermalization sweeps, then measured sweeps."""
+    p = mc.parameters
+    if not mc._initialized:
+        mc.init()
+    t0 = time.time()
+    total = p.thermalization + p.sweeps
+    for i in range(mc.last_sweep + 1, total + 1):
+        mc.sweep_once()
+        if i > p.thermalization and (i - p.thermalization) % p.measure_rate == 0 and mc.measurements:
+            G = mc.ctx.measured_greens()
+            for m in mc.measurements.values():
+                m.push(G)
+        if verbose and i % p.print_rate == 0:
+            rate = mc.accepted.sum() / max(mc.total * mc.ctx.B, 1)
+            print(f"\t{i}\n\t\tsweep dur: {(time.time() - t0) / i:.3f}s\n\t\tacc rate (local): {rate:.3f}")
+        if i == p.thermalization and p.thermalization > 0:
+            rate = mc.accepted.sum() / max(mc.total * mc.ctx.B, 1)
+            if rate < min_update_rate:
+                mc.sync_field()
+                return "CANCELLED_LOW_ACCEPTANCE"        # DQMC.jl:294-307, helpers.jl:17-22
+    mc.sync_field()
+    return "SUCCESS"
+
+
+run_b = run
