@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- DQMC sweeps/sec (all chains) on N B200s, with roofline, CPU baseline and e2e.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4] [--chains B] [--impl reference]
+
+One "step" = one full local sweep (2M slice visits x N proposals, all wraps and stabilisations,
+reference local_updates.jl:7-14) of every chain of the context.  Default workload = BASELINE.json
+configs[3] ("cfg4": repulsive Hubbard 16x16, beta=16, dtau=0.1 -- the configuration the north_star
+target is quoted on); the other configs are selectable and are parity-test cases.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CONFIGS = {
+    # name: (lattice, Ls, U, beta, chains per GPU, description)
+    "cfg1": ("square", (4, 4), 4.0, 5.0, 1, "attractive Hubbard 4x4, U=4, beta=5, single chain"),
+    "cfg2": ("square", (8, 8), 4.0, 10.0, 256, "attractive Hubbard 8x8, U=4, beta=10, 256 chains/GPU"),
+    "cfg3": ("square", (12, 12), -4.0, 8.0, 128, "repulsive Hubbard 12x12, U=-4, beta=8, 128 chains/GPU"),
+    "cfg4": ("square", (16, 16), -4.0, 16.0, 148, "repulsive Hubbard 16x16, U=-4, beta=16, dtau=0.1 (N=256, M=160)"),
+    "cfg5": ("honeycomb", (12, 12), 4.0, 10.0, 64, "attractive Hubbard honeycomb L=12 (N=288), U=4, beta=10"),
+}
+DELTA_TAU, SAFE_MULT, SEED = 0.1, 10, 1234
+
+
+def flops_per_sweep(n, M, C, nb, acc_rate):
+    """F_sweep = nb n^3 (12 M + 44 C + 4 a M) [+ 4 C n^3 nb for the check wrap]."""
+    return nb * float(n) ** 3 * (12 * M + 44 * C + 4 * acc_rate * M + 4 * C)
+
+
+def build_model(cfg):
+    from oracle import model as OM   # model *inputs* only (lattice -> T); not on the measured path
+    kind, Ls, U, beta, B, desc = CONFIGS[cfg]
+    return kind, Ls, U, beta, B, desc
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------
+def run_cpu(cfg, steps, warmup, max_chains=None):
+    from oracle import model as OM, ref as OR
+    kind, Ls, U, beta, _, desc = build_model(cfg)
+    T = OM.hopping_matrix(kind, Ls)
+    N, M = T.shape[0], OM.n_slices(beta, DELTA_TAU)
+    cores = OR.lib().ref_max_threads()
+    nch = cores if max_chains is None else min(cores, max_chains)
+    g = np.random.default_rng(SEED)
+    chains = [OR.RefChain(T, U=U, beta=beta, delta_tau=DELTA_TAU, safe_mult=SAFE_MULT, seed=SEED, chain_id=b,
+                          conf=np.asfortranarray(g.choice(np.array([-1, 1], dtype=np.int8), size=(N, M))))
+              for b in range(nch)]
+    dt, acc = OR.run_chains(chains, nthreads=nch, warm=warmup, nsweeps=steps)
+    a = float(acc.sum()) / (steps * nch * 2 * N * M)
+    return {"value": nch * steps / dt, "seconds": dt, "cores": nch, "chains": nch, "sweeps_per_chain": steps,
+            "acceptance": a, "N": N, "M": M, "nb": chains[0].nb, "C": chains[0].C}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.split(",") for l in Path(self.f.name).read_text().splitlines() if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default=os.environ.get("DQMC_BENCH_CONFIG", "cfg4"), choices=sorted(CONFIGS))
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = config default)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--delay-block", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-pass", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    kind, Ls, U, beta, Bdef, desc = build_model(args.config)
+    B = args.chains or Bdef
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warm = max(1, args.steps), 0 if args.config in ("cfg3", "cfg4", "cfg5") else min(args.warmup, 1)
+        r = run_cpu(args.config, steps, warm)
+        line = {"impl": "reference", "metric": "DQMC sweeps/sec (all chains)", "value": r["value"], "unit": "sweeps/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * r["seconds"] / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{args.config}: {desc}", "chains": r["chains"], "delta_tau": DELTA_TAU,
+                           "safe_mult": SAFE_MULT},
+                "cpu_baseline": {"value": r["value"], "unit": "sweeps/s", "cores": r["cores"], "kind": "port",
+                                 "sample": f"{r['chains']} chains (one per host core) x {steps} sweep(s); C port of the "
+                                           "reference's loops (oracle/dqmc_ref.c) -- Julia is not in the image"},
+                "e2e": {"value": r["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "acceptance": r["acceptance"], "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import _b200_loader
+    pkg = _b200_loader.load()
+    from oracle import model as OM     # lattice -> hopping matrix inputs only
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the dqmc_b200 path has no CPU fallback")
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+
+    T = OM.hopping_matrix(kind, Ls)
+    N, M = T.shape[0], OM.n_slices(beta, DELTA_TAU)
+    fk = OM.choose_field(U)
+    nb = 1 if fk == 0 else 2
+    ranges = OM.generate_chunks(M, SAFE_MULT)
+    C = len(ranges)
+    e2, e2i, eh, ehi = OM.hopping_exponentials(T, DELTA_TAU)
+    g = np.random.default_rng(SEED + rank)
+    conf = np.asfortranarray(g.choice(np.array([-1, 1], dtype=np.int8), size=(N, M, B)))
+    ctx = pkg.Context(n_sites=N, n_slices=M, field_kind=fk, n_chains=B, ranges=ranges,
+                      alpha=OM.hirsch_alpha(U, DELTA_TAU, fk), hopping_exp_squared=e2, hopping_exp_inv_squared=e2i,
+                      hopping_exp=eh, hopping_exp_inv=ehi, seed=SEED, chain_offset=rank * B, device=dev,
+                      delay_block=args.delay_block)
+    ctx.set_conf(conf)
+    ctx.build_stack()
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def sum_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+        return x
+
+    W, K = max(3, args.warmup), max(1, args.steps)
+    for _ in range(W):
+        ctx.sweep(1)
+
+    # ---------------- timed region 1: device-resident sweeps ---------------------------------
+    clocks = Clocks(dev)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    acc_total = 0
+    for _ in range(K):
+        acc_total += int(ctx.sweep(1).sum())
+    ctx.accumulate_greens()
+    if world > 1:      # the only collective of the path: final observable reduction over NVLink
+        buf = ctx.observable_tensor(torch)
+        dist.all_reduce(buf)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.kernel_launches() - l0
+    clk = clocks.stop() if rank == 0 else None
+    acc_rate = sum_over_ranks(acc_total) / (world * B * K * 2.0 * N * M)
+    value = world * B * K / (ms * 1e-3)
+
+    # ---------------- timed region 2: end to end through the C ABI with host buffers ---------
+    u_host = torch.empty((B, 2 * M, N), dtype=torch.float64).pin_memory()
+    g_host = torch.empty((B, nb, N, N), dtype=torch.float64).pin_memory()
+    c_host = torch.empty((B, M, N), dtype=torch.int8).pin_memory()
+    rng_t = torch.Generator().manual_seed(SEED + 17 * rank)
+    u_host.uniform_(generator=rng_t)     # the host's own RNG stream (drop-in mode: Julia supplies the uniforms)
+    barrier()
+    e2e0, e2e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e0.record(stream)
+    for _ in range(K):
+        ctx.sweep(1, uniforms=u_host.numpy())                    # H2D of this sweep's uniforms inside the call
+        ctx.greens(out=g_host.numpy())                           # D2H: mc.stack.greens of every chain
+        ctx.get_conf(out=c_host.numpy())                         # D2H: field.conf of every chain
+    e2e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e2e0.elapsed_time(e2e1))
+    e2e_value = world * B * K / (ms_e2e * 1e-3)
+    h2d = u_host.numel() * 8
+    d2h = g_host.numel() * 8 + c_host.numel() + B * 8
+
+    # ---------------- roofline pass: per-launch CUDA events on the launching stream -----------
+    roof = None
+    if not args.no_kernel_pass:
+        ctx.profile(True)
+        for _ in range(K):
+            ctx.sweep(1)
+        prof = ctx.profile_report()
+        ctx.profile(False)
+        p64 = measure_fp64_peak(torch) if rank == 0 else None
+        if rank == 0:
+            gm = prof["gemm"]
+            flops_per_launch = 2.0 * N ** 3 * B * nb        # every GEMM launch of the sweep is n x n x n over all matrices
+            avg_ms = gm["ms"] / max(gm["count"], 1)
+            achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
+            total_ms = sum(v["ms"] for v in prof.values())
+            roof = {"bound": "tensor", "kernel": "gemm_kernel (FP64 DMMA batched GEMM)", "achieved": achieved,
+                    "peak": p64, "unit": "TFLOP/s", "frac": achieved / p64 if p64 else None, "traffic": None,
+                    "peak_source": "measured in this run: cuBLAS DGEMM (torch.matmul f64 8192^3, best of 5); "
+                                   "MEASURED_PEAKS.json has no FP64 entry",
+                    "launches": gm["count"], "avg_launch_ms": avg_ms,
+                    "share_of_step": gm["ms"] / total_ms if total_ms else None,
+                    "kernel_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
+                    "whole_sweep_frac_of_fp64_peak": (flops_per_sweep(N, M, C, nb, acc_rate) * value / 1e12) / p64 if p64 else None}
+
+    line = None
+    if rank == 0:
+        line = {"metric": "DQMC sweeps/sec (all chains)", "value": value, "unit": "sweeps/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{args.config}: {desc}", "chains_per_gpu": B, "n_sites": N, "n_slices": M,
+                           "flavor_blocks": nb, "delta_tau": DELTA_TAU, "safe_mult": SAFE_MULT, "U": U,
+                           "l2": "inputs larger than L2 (per-GPU state %.1f GB)" % (ctx_bytes(N, M, C, nb, B) / 1e9),
+                           "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
+                "acceptance": acc_rate, "gpu_launches": int(launches), "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K},
+                "roofline": roof,
+                "flops_per_sweep_per_chain": flops_per_sweep(N, M, C, nb, acc_rate)}
+        if world == 1 and not args.no_cpu_baseline:
+            r = run_cpu(args.config, 1, 0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "sweeps/s", "cores": r["cores"], "kind": "port",
+                                    "sample": f"{r['chains']} chains (one per host core) x 1 sweep each of the same "
+                                              f"workload, {r['seconds']:.1f} s; oracle/dqmc_ref.c (C port, Julia absent)"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ctx_bytes(N, M, C, nb, B):
+    ld = (N + 1) & ~1
+    mat = B * nb * ld * N * 8
+    return mat * (2 * (C + 1) + 11) + B * M * N
+
+
+def measure_fp64_peak(torch, n=8192):
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    best = 1e30
+    for _ in range(5):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); torch.matmul(a, b); e.record(); e.synchronize()
+        best = min(best, s.elapsed_time(e))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+if __name__ == "__main__":
+    main()

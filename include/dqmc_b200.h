@@ -156,6 +156,19 @@ int32_t dqmc_op_multiply_slice_matrix(dqmc_ctx* ctx, int32_t which, int32_t slic
 int32_t dqmc_op_wrap_greens(dqmc_ctx* ctx, int32_t curr_slice, int32_t direction, double* X);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
+/* the CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that the
+ * host can bracket calls with its own CUDA events. */
+int32_t dqmc_get_stream(dqmc_ctx* ctx, void** cuda_stream);
+/* per-launch CUDA-event timing by kernel category (the @bm TimerOutputs hooks of the reference,
+ * src/helpers.jl:83-104).  enable != 0 resets the counters and starts recording. */
+#define DQMC_PROF_GEMM 0     /* n x n x n batched DMMA GEMMs (vmul!, slice matrices, wraps)     */
+#define DQMC_PROF_UDT 1      /* udt_AVX_pivot!                                                   */
+#define DQMC_PROF_RDIVP 2    /* rdivp! (permute + panel GEMMs + diagonal-block solves)           */
+#define DQMC_PROF_UPDATE 3   /* sweep_spatial                                                    */
+#define DQMC_PROF_OTHER 4    /* copies, identity fills, propagation-error reduction             */
+#define DQMC_PROF_NCAT 5
+int32_t dqmc_profile(dqmc_ctx* ctx, int32_t enable);
+int32_t dqmc_profile_report(dqmc_ctx* ctx, double* ms /* [DQMC_PROF_NCAT] */, int64_t* count /* [DQMC_PROF_NCAT] */);
 /* number of CUDA kernels this context has launched so far. */
 int64_t dqmc_kernel_launches(const dqmc_ctx* ctx);
 /* largest n_sites the UDT kernel supports in this build. */

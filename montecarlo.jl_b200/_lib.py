@@ -86,6 +86,9 @@ def load():
         "dqmc_op_calculate_greens": (i32, [i32, i32, i32, dp, dp, dp, dp, dp, dp, dp]),
         "dqmc_op_multiply_slice_matrix": (i32, [vp, i32, i32, dp]),
         "dqmc_op_wrap_greens": (i32, [vp, i32, i32, dp]),
+        "dqmc_get_stream": (i32, [vp, C.POINTER(vp)]),
+        "dqmc_profile": (i32, [vp, i32]),
+        "dqmc_profile_report": (i32, [vp, dp, i64p]),
         "dqmc_kernel_launches": (i64, [vp]),
         "dqmc_max_sites": (i32, []),
     }

@@ -93,9 +93,12 @@ class Context:
         assert conf.shape[:2] == (self.N, self.M)
         self._ck(self._L.dqmc_set_conf(self._h, chain0, conf.shape[2], conf.ctypes.data_as(_lib.i8p)))
 
-    def get_conf(self, chain0=0, nchains=None):
+    def get_conf(self, chain0=0, nchains=None, out=None):
+        """out: optional preallocated (e.g. pinned) int8 buffer of N*M*nchains bytes."""
         nchains = self.B - chain0 if nchains is None else nchains
-        out = np.zeros((self.N, self.M, nchains), dtype=np.int8, order="F")
+        if out is None:
+            out = np.zeros((self.N, self.M, nchains), dtype=np.int8, order="F")
+        assert out.dtype == np.int8 and out.size == self.N * self.M * nchains
         self._ck(self._L.dqmc_get_conf(self._h, chain0, nchains, out.ctypes.data_as(_lib.i8p)))
         return out
 
@@ -167,9 +170,12 @@ class Context:
     def _gshape(self, nchains):
         return (self.N, self.N, self.nb, nchains)
 
-    def greens(self, chain0=0, nchains=None):
+    def greens(self, chain0=0, nchains=None, out=None):
+        """out: optional preallocated (e.g. pinned) float64 buffer of N*N*nb*nchains elements."""
         nchains = self.B - chain0 if nchains is None else nchains
-        out = np.zeros(self._gshape(nchains), order="F")
+        if out is None:
+            out = np.zeros(self._gshape(nchains), order="F")
+        assert out.dtype == np.float64 and out.size == self.N * self.N * self.nb * nchains
         self._ck(self._L.dqmc_get_greens(self._h, chain0, nchains, _dp(out)))
         return out
 
@@ -234,6 +240,31 @@ class Context:
 
     def kernel_launches(self):
         return int(self._L.dqmc_kernel_launches(self._h))
+
+    def stream_handle(self):
+        """cudaStream_t of the context as an integer (torch.cuda.ExternalStream(handle))."""
+        p = C.c_void_p()
+        self._ck(self._L.dqmc_get_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    PROF_NAMES = ("gemm", "udt", "rdivp", "update", "other")
+
+    def profile(self, enable=True):
+        self._ck(self._L.dqmc_profile(self._h, int(enable)))
+
+    def profile_report(self):
+        ms = np.zeros(len(self.PROF_NAMES)); cnt = np.zeros(len(self.PROF_NAMES), dtype=np.int64)
+        self._ck(self._L.dqmc_profile_report(self._h, _dp(ms), cnt.ctypes.data_as(_lib.i64p)))
+        return {n: {"ms": float(ms[i]), "count": int(cnt[i])} for i, n in enumerate(self.PROF_NAMES)}
+
+    def observable_tensor(self, torch):
+        """The device accumulator block [count | sum | sumsq] as a torch tensor (no copy), for
+        torch.distributed.all_reduce over NCCL."""
+        ptr, n = self.observable_buffer()
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Buf(), device="cuda")
 
 
 # ---------------------------------------------------------------------- operator level, stateless

@@ -52,6 +52,32 @@ struct dqmc_ctx {
     long long sweep_index = 0;
     std::string err;
     std::vector<void*> allocs;
+    // per-category CUDA-event profiler
+    bool prof_on = false; int prof_depth = 0;
+    std::vector<cudaEvent_t> prof_pool; size_t prof_used = 0;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_spans;
+};
+
+static cudaEvent_t prof_event(dqmc_ctx* c)
+{
+    if (c->prof_used == c->prof_pool.size()) {
+        cudaEvent_t e; cudaEventCreate(&e); c->prof_pool.push_back(e);
+    }
+    return c->prof_pool[c->prof_used++];
+}
+// times the outermost category only (rdivp! contains GEMM launches of its own)
+struct ProfScope {
+    dqmc_ctx* c; cudaEvent_t e1 = nullptr; bool active;
+    ProfScope(dqmc_ctx* ctx, int cat) : c(ctx), active(ctx->prof_on && ctx->prof_depth == 0)
+    {
+        ++c->prof_depth;
+        if (active) {
+            cudaEvent_t e0 = prof_event(c); e1 = prof_event(c);
+            cudaEventRecord(e0, c->st);
+            c->prof_spans.push_back({cat, {e0, e1}});
+        }
+    }
+    ~ProfScope() { --c->prof_depth; if (active) cudaEventRecord(e1, c->st); }
 };
 
 #define FAIL(ctx, code, msg) do { (ctx)->err = (msg); return (code); } while (0)
@@ -118,6 +144,7 @@ static cudaError_t mm(dqmc_ctx* c, double* dst, const double* A, bool tA, bool s
                       bool sharedB, Scale rs = no_scale(), Scale ks = no_scale(), Scale cs = no_scale(),
                       const double* add_diag = nullptr)
 {
+    ProfScope ps(c, DQMC_PROF_GEMM);
     GemmParams g = gemm_base(c);
     g.A = A; g.transA = tA; if (sharedA) g.strideA = 0;
     g.B = Bm; g.transB = tB; if (sharedB) g.strideB = 0;
@@ -152,6 +179,7 @@ static cudaError_t wrap_greens(dqmc_ctx* c, double* gf, double* tmp, int curr_sl
 
 static cudaError_t udt(dqmc_ctx* c, const double* A, Scale colscale, double* U, double* D, double* T, bool apply_pivot)
 {
+    ProfScope ps(c, DQMC_PROF_UDT);
     UdtParams p{};
     p.n = c->N; p.ld = c->ld; p.batch = c->nmat;
     p.A = A; p.strideA = c->ms; p.colscale = colscale;
@@ -163,6 +191,7 @@ static cudaError_t udt(dqmc_ctx* c, const double* A, Scale colscale, double* U, 
 
 static cudaError_t rdivp(dqmc_ctx* c, double* A, const double* T, double* work)
 {
+    ProfScope ps(c, DQMC_PROF_RDIVP);
     RdivpParams p{};
     p.n = c->N; p.ld = c->ld; p.batch = c->nmat;
     p.A = A; p.strideA = c->ms; p.T = T; p.strideT = c->ms;
@@ -171,11 +200,11 @@ static cudaError_t rdivp(dqmc_ctx* c, double* A, const double* T, double* work)
 }
 
 static cudaError_t copy_mats(dqmc_ctx* c, double* dst, const double* src)
-{ return cudaMemcpyAsync(dst, src, (size_t)c->nmat * c->ms * 8, cudaMemcpyDeviceToDevice, c->st); }
+{ ProfScope ps(c, DQMC_PROF_OTHER); return cudaMemcpyAsync(dst, src, (size_t)c->nmat * c->ms * 8, cudaMemcpyDeviceToDevice, c->st); }
 static cudaError_t copy_vecs(dqmc_ctx* c, double* dst, const double* src)
-{ return cudaMemcpyAsync(dst, src, (size_t)c->nmat * c->N * 8, cudaMemcpyDeviceToDevice, c->st); }
-static cudaError_t ident(dqmc_ctx* c, double* A) { return launch_set_identity(A, c->N, c->ld, c->ms, c->nmat, c->st); }
-static cudaError_t ones(dqmc_ctx* c, double* v) { return launch_fill(v, 1.0, (long long)c->nmat * c->N, c->st); }
+{ ProfScope ps(c, DQMC_PROF_OTHER); return cudaMemcpyAsync(dst, src, (size_t)c->nmat * c->N * 8, cudaMemcpyDeviceToDevice, c->st); }
+static cudaError_t ident(dqmc_ctx* c, double* A) { ProfScope ps(c, DQMC_PROF_OTHER); return launch_set_identity(A, c->N, c->ld, c->ms, c->nmat, c->st); }
+static cudaError_t ones(dqmc_ctx* c, double* v) { ProfScope ps(c, DQMC_PROF_OTHER); return launch_fill(v, 1.0, (long long)c->nmat * c->N, c->st); }
 
 #define CE(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return e__; } while (0)
 
@@ -239,12 +268,13 @@ static cudaError_t load_udt(dqmc_ctx* c, double* U, double* D, double* T, int sl
 static cudaError_t clear_slot(dqmc_ctx* c, int slot)
 {
     CE(ident(c, slot_mat(c, c->u_stack, slot)));
-    CE(launch_fill(slot_vec(c, c->d_stack, slot), 1.0, (long long)c->nmat * c->N, c->st));
+    { ProfScope ps(c, DQMC_PROF_OTHER); CE(launch_fill(slot_vec(c, c->d_stack, slot), 1.0, (long long)c->nmat * c->N, c->st)); }
     return ident(c, slot_mat(c, c->t_stack, slot));
 }
 
 static cudaError_t prop_check(dqmc_ctx* c)
 {
+    ProfScope ps(c, DQMC_PROF_OTHER);
     return launch_prop_error(c->greens_temp, c->greens, c->N, c->ld, (long long)c->nb * c->ms, c->nb, c->B, 1e-7,
                              c->stats_prop, c->st);
 }
@@ -322,6 +352,7 @@ static cudaError_t sweep_spatial(dqmc_ctx* c, int step, const double* d_unif, lo
                                  const unsigned char* d_forced, double* d_probs, unsigned char* d_dec,
                                  long long tstride)
 {
+    ProfScope ps(c, DQMC_PROF_UPDATE);
     UpdateParams p{};
     p.n = c->N; p.ld = c->ld; p.nb = c->nb; p.kind = c->kind; p.n_chains = c->B;
     p.G = c->greens; p.strideG = c->ms;
@@ -382,6 +413,7 @@ int32_t dqmc_destroy(dqmc_ctx* c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     for (void* p : c->allocs) cudaFree(p);
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
@@ -609,6 +641,36 @@ int32_t dqmc_sweep_spatial(dqmc_ctx* c, const double* uniforms, const uint8_t* f
     if (probs) CK(c, cudaMemcpyAsync(probs, c->d_probs, cnt * 8, cudaMemcpyDeviceToHost, c->st));
     if (decisions) CK(c, cudaMemcpyAsync(decisions, c->d_dec, cnt, cudaMemcpyDeviceToHost, c->st));
     return fetch_accepted(c, accepted);
+}
+
+int32_t dqmc_get_stream(dqmc_ctx* c, void** stream)
+{
+    if (!c || !stream) return DQMC_ERR_INVALID;
+    *stream = (void*)c->st;
+    return DQMC_OK;
+}
+
+int32_t dqmc_profile(dqmc_ctx* c, int32_t enable)
+{
+    ENTER(c);
+    CK(c, cudaStreamSynchronize(c->st));
+    c->prof_on = enable != 0;
+    if (enable) { c->prof_spans.clear(); c->prof_used = 0; }
+    return DQMC_OK;
+}
+
+int32_t dqmc_profile_report(dqmc_ctx* c, double* ms, int64_t* count)
+{
+    ENTER(c);
+    if (!ms || !count) FAIL(c, DQMC_ERR_INVALID, "dqmc_profile_report: bad arguments");
+    CK(c, cudaStreamSynchronize(c->st));
+    for (int i = 0; i < DQMC_PROF_NCAT; ++i) { ms[i] = 0.0; count[i] = 0; }
+    for (auto& sp : c->prof_spans) {
+        float t = 0.f;
+        CK(c, cudaEventElapsedTime(&t, sp.second.first, sp.second.second));
+        ms[sp.first] += (double)t; count[sp.first] += 1;
+    }
+    return DQMC_OK;
 }
 
 int32_t dqmc_get_greens(dqmc_ctx* c, int32_t chain0, int32_t nchains, double* G)
