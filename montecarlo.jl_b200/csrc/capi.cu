@@ -31,7 +31,7 @@ struct dqmc_ctx {
     double alpha = 0.0;
     int check_sign = 1, check_prop = 1;
     unsigned long long seed = 0; long long chain_offset = 0; int device = 0; int kb = 0;
-    int ld = 0; long long ms = 0; int nmat = 0;
+    int ld = 0; long long ms = 0; int nmat = 0; int ldv = 0;
     cudaStream_t st = nullptr;
     // device state
     double *eT2 = nullptr, *eT2i = nullptr, *eTh = nullptr, *eThi = nullptr;
@@ -185,7 +185,7 @@ static cudaError_t udt(dqmc_ctx* c, const double* A, Scale colscale, double* U, 
     p.A = A; p.strideA = c->ms; p.colscale = colscale;
     p.U = U; p.strideU = c->ms; p.D = D; p.strideD = c->N; p.T = T; p.strideT = c->ms;
     p.pivot = c->pivot; p.stridePivot = c->N; p.pivot_applied = apply_pivot ? 1 : 0;
-    p.Vwork = c->Vwork; p.strideV = c->ms; p.tau = c->tau; p.strideTau = c->N;
+    p.Vwork = c->Vwork; p.ldv = c->ldv; p.strideV = (long long)c->ldv * c->N; p.tau = c->tau; p.strideTau = c->N;
     return launch_udt(p, c->st);
 }
 
@@ -461,6 +461,7 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     c->alpha = d->alpha; c->check_sign = d->check_sign_problem; c->check_prop = d->check_propagation_error;
     c->seed = d->seed; c->chain_offset = d->chain_offset; c->device = d->device;
     c->ld = (c->N + 1) & ~1; c->ms = (long long)c->ld * c->N; c->nmat = c->B * c->nb;
+    c->ldv = ((c->N + 31) / 32) * 32;
     c->kb = d->delay_block > 0 ? ((d->delay_block + 3) & ~3) : update_pick_kb(c->N, c->nb);
     {
         const int kmax = update_pick_kb(c->N, c->nb);
@@ -479,7 +480,7 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     A_(conf, (size_t)c->B * c->M * c->N);
     A_(u_stack, mat * (c->C + 1)); A_(t_stack, mat * (c->C + 1)); A_(d_stack, vec * (c->C + 1));
     A_(greens, mat); A_(greens_temp, mat); A_(Ul, mat); A_(Ur, mat); A_(Tl, mat); A_(Tr, mat);
-    A_(tmp1, mat); A_(tmp2, mat); A_(curr_U, mat); A_(Vwork, mat);
+    A_(tmp1, mat); A_(tmp2, mat); A_(curr_U, mat); A_(Vwork, (size_t)c->nmat * c->ldv * c->N);
     A_(Dl, vec); A_(Dr, vec); A_(tau, vec);
     A_(pivot, vec); A_(accepted, (size_t)c->B);
     A_(stats_neg, (size_t)c->B * 4); A_(stats_prop, (size_t)c->B * 4);
@@ -853,7 +854,7 @@ static int32_t make_op_ctx(int device, int n, int batch, dqmc_ctx** out)
     cudaSetDevice(device);
     dqmc_ctx* c = new dqmc_ctx();
     c->N = n; c->M = 1; c->nb = 1; c->B = batch; c->C = 1; c->device = device;
-    c->ld = (n + 1) & ~1; c->ms = (long long)c->ld * n; c->nmat = batch;
+    c->ld = (n + 1) & ~1; c->ms = (long long)c->ld * n; c->nmat = batch; c->ldv = ((n + 31) / 32) * 32;
     cudaError_t e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
     const size_t mat = (size_t)c->nmat * c->ms, vec = (size_t)c->nmat * n;
     if (e == cudaSuccess) e = dalloc(c, &c->greens, mat);
@@ -862,7 +863,7 @@ static int32_t make_op_ctx(int device, int n, int batch, dqmc_ctx** out)
     if (e == cudaSuccess) e = dalloc(c, &c->Tl, mat);
     if (e == cudaSuccess) e = dalloc(c, &c->Tr, mat);
     if (e == cudaSuccess) e = dalloc(c, &c->tmp1, mat);
-    if (e == cudaSuccess) e = dalloc(c, &c->Vwork, mat);
+    if (e == cudaSuccess) e = dalloc(c, &c->Vwork, (size_t)c->nmat * c->ldv * n);
     if (e == cudaSuccess) e = dalloc(c, &c->Dl, vec);
     if (e == cudaSuccess) e = dalloc(c, &c->Dr, vec);
     if (e == cudaSuccess) e = dalloc(c, &c->tau, vec);

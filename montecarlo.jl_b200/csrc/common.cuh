@@ -63,7 +63,7 @@ struct UdtParams {
     double* T; long long strideT;            // pivot_applied: D^-1 R P^T ; else clean upper-triangular D^-1 R (logical order)
     int* pivot; long long stridePivot;       // logical column j came from input column pivot[j] (0-based)
     int pivot_applied;
-    double* Vwork; long long strideV;        // n x ld scratch per matrix (Householder vectors)
+    double* Vwork; long long strideV; int ldv; // n columns x ldv (>= 32 * ceil(n/32)) scratch per matrix (Householder vectors)
     double* tau; long long strideTau;        // n scratch per matrix
 };
 cudaError_t launch_udt(const UdtParams& p, cudaStream_t st);

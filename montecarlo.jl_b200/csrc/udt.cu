@@ -22,6 +22,7 @@
 // Q is then accumulated backwards over the same resident layout.
 // Roofline: shared-memory bandwidth / FP64 FMA (level-2 work), see DESIGN.md.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -182,7 +183,7 @@ __global__ void udt_kernel(const UdtParams p, const UdtGeom gm)
             // the reference divides (x[i] /= xi1); keep the division for bit-closeness
             const double x = (bv == 0.0) ? 0.0 : raw[i] / xi1;
             v[i] = x;
-            if (rank == br) Vg[i + (long long)j * p.ld] = x;
+            if (rank == br) Vg[i + (long long)j * p.ldv] = x;
         }
         if (tid == 0) {
             const double ad = fabs(rjj);
@@ -257,7 +258,7 @@ __global__ void udt_kernel(const UdtParams p, const UdtGeom gm)
     for (int k = n - 1; k >= 0; --k) {
         double* vk = vcur + (k & 1) * nv;
         // load v_k (rows k+1..n-1) -- for k == n-1 the range is empty
-        for (int i = k + 1 + tid; i < n; i += NT) vk[i] = Vg[i + (long long)k * p.ld];
+        for (int i = k + 1 + tid; i < n; i += NT) vk[i] = Vg[i + (long long)k * p.ldv];
         __syncthreads();
         const double tau = taus[k];
         for (int pass = 0; pass < npass; ++pass) {
@@ -293,9 +294,15 @@ __global__ void udt_kernel(const UdtParams p, const UdtGeom gm)
     }
 }
 
+bool udt_reg_supported(int n);
+cudaError_t launch_udt_reg(const UdtParams& p, cudaStream_t st);
+
 cudaError_t launch_udt(const UdtParams& p, cudaStream_t st)
 {
     if (p.batch <= 0) return cudaSuccess;
+    // v2: register-resident panel (udt_reg.cu); v1 (shared-memory panel, below) covers larger n
+    static const bool force_v1 = getenv("DQMC_UDT_V1") != nullptr;
+    if (!force_v1 && udt_reg_supported(p.n)) return launch_udt_reg(p, st);
     const UdtGeom g = udt_geometry(p.n);
     if (g.smem > 220 * 1024) return cudaErrorInvalidConfiguration;
     static size_t configured = 0;

@@ -30,12 +30,23 @@ __device__ __forceinline__ void dmma884u(double& c0, double& c1, double a, doubl
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(a), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
 static inline int update_ldu(int n) { return n + (((4 - n) % 16) + 16) % 16; }   // == 4 mod 16
 
 int update_pick_kb(int n, int nb)
 {
     const long long per_slot = (long long)nb * 2 * update_ldu(n) * 8;
-    long long kb = (200LL * 1024) / per_slot;
+    long long kb = (200LL * 1024 - 9LL * n) / per_slot;
     if (kb > 32) kb = 32;
     kb &= ~3LL;
     if (kb < 4) kb = 4;
@@ -58,14 +69,19 @@ __global__ void update_kernel(const UpdateParams p, const int ldu, const double 
     double* Uc = sm;                                   // [nb][kb][ldu]   columns of G0 -> u_a
     double* Wr = Uc + (size_t)nb * kb * ldu;           // [nb][kb][ldu]   rows of G0    -> w_a
     UpdShared* sh = (UpdShared*)(Wr + (size_t)nb * kb * ldu);
-    int8_t* sconf = (int8_t*)(sh + 1);                 // [n]
+    double* sunif = (double*)(sh + 1);                 // [n] Metropolis uniforms of this slice visit
+    int8_t* sconf = (int8_t*)(sunif + n);              // [n]
 
     double* G = p.G + (long long)chain * nb * p.strideG;
     int8_t* conf = p.conf_slice + (long long)chain * p.cstride;
     const double* utab = p.uniforms ? p.uniforms + (long long)chain * p.ustride : nullptr;
     const unsigned char* forced = p.forced ? p.forced + (long long)chain * p.tstride : nullptr;
 
-    for (int i = tid; i < n; i += NT) sconf[i] = conf[i];
+    for (int i = tid; i < n; i += NT) {
+        sconf[i] = conf[i];
+        sunif[i] = utab ? utab[i]
+                        : dqmc_uniform(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)p.sweep, (uint32_t)p.step, (uint32_t)i);
+    }
 
     int accepted = 0;                  // tracked by every thread identically
     double neg_cnt = 0.0, neg_sum = 0.0, neg_min = INFINITY, neg_max = -INFINITY;   // lane 0 of warp 0
@@ -80,13 +96,14 @@ __global__ void update_kernel(const UpdateParams p, const int ldu, const double 
             double* wb = Wr + (size_t)b * kb * ldu;
             for (int e = tid; e < kbc * n; e += NT) {
                 const int j = e / n, r = e - j * n;
-                ub[(size_t)j * ldu + r] = Gb[r + (long long)(i0 + j) * ld];
+                cp_async8(ub + (size_t)j * ldu + r, Gb + r + (long long)(i0 + j) * ld);
             }
             for (int e = tid; e < kbc * n; e += NT) {
                 const int c = e / kbc, j = e - c * kbc;
-                wb[(size_t)j * ldu + c] = Gb[(i0 + j) + (long long)c * ld];
+                cp_async8(wb + (size_t)j * ldu + c, Gb + (i0 + j) + (long long)c * ld);
             }
         }
+        cp_async_wait_all();
         __syncthreads();
 
         int k = 0;                     // accepted flips in this block (delayed factors in slots 0..k-1)
@@ -102,9 +119,10 @@ __global__ void update_kernel(const UpdateParams p, const int ldu, const double 
                 for (int b = 0; b < nb; ++b) {
                     const double* ub = Uc + (size_t)b * kb * ldu;
                     const double* wb = Wr + (size_t)b * kb * ldu;
+                    // slots a < k hold -u_a (negated so that the flush needs no FP64 negation)
                     double part = (lane < k) ? ub[(size_t)lane * ldu + i] * wb[(size_t)lane * ldu + i] : 0.0;
                     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                    const double gii = ub[(size_t)j * ldu + i] - part;
+                    const double gii = ub[(size_t)j * ldu + i] + part;
                     Dl[b] = ((p.kind == 1 && b == 1) ? e_mdE : e_dE) - 1.0;
                     Rv[b] = 1.0 + Dl[b] * (1.0 - gii);
                 }
@@ -120,10 +138,7 @@ __global__ void update_kernel(const UpdateParams p, const int ldu, const double 
                     if (forced) acc = forced[i] != 0;
                     else if (prob > 1.0) acc = 1;
                     else {
-                        const double u = utab ? utab[i]
-                                              : dqmc_uniform(p.seed, (uint64_t)(p.chain0 + chain),
-                                                             (uint64_t)p.sweep, (uint32_t)p.step, (uint32_t)i);
-                        acc = u < prob;
+                        acc = sunif[i] < prob;
                     }
                     if (p.probs) p.probs[(long long)chain * p.tstride + i] = prob;
                     if (p.decisions) p.decisions[(long long)chain * p.tstride + i] = (unsigned char)acc;
@@ -144,11 +159,11 @@ __global__ void update_kernel(const UpdateParams p, const int ldu, const double 
                         double col = ub[(size_t)j * ldu + r];
                         double row = wb[(size_t)j * ldu + r];
                         for (int a = 0; a < k; ++a) {
-                            col -= ub[(size_t)a * ldu + r] * wb[(size_t)a * ldu + i];
-                            row -= ub[(size_t)a * ldu + i] * wb[(size_t)a * ldu + r];
+                            col += ub[(size_t)a * ldu + r] * wb[(size_t)a * ldu + i];
+                            row += ub[(size_t)a * ldu + i] * wb[(size_t)a * ldu + r];
                         }
                         // element (slot k, r) is only ever touched by this thread until the barrier
-                        ub[(size_t)k * ldu + r] = ((r == i) ? 1.0 : 0.0) - col;
+                        ub[(size_t)k * ldu + r] = col - ((r == i) ? 1.0 : 0.0);     // -u = G[:, i] - e_i
                         wb[(size_t)k * ldu + r] = coef * row;
                     }
                 }
@@ -171,11 +186,19 @@ __global__ void update_kernel(const UpdateParams p, const int ldu, const double 
                 const double* wb = Wr + (size_t)b * kb * ldu;
                 for (int tile = warp; tile < tiles * tiles; tile += nwarps) {
                     const int tm = (tile % tiles) * 32, tn = (tile / tiles) * 32;
+                    // acc <- G tile (all loads in flight together), then acc += (-u) w^T, then store
                     double acc2[4][4][2];
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi)
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const int r = tm + mi * 8 + g;
 #pragma unroll
-                        for (int nj = 0; nj < 4; ++nj) acc2[mi][nj][0] = acc2[mi][nj][1] = 0.0;
+                        for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = tn + nj * 8 + 2 * t + e;
+                                acc2[mi][nj][e] = (r < n && c < n) ? Gb[r + (long long)c * ld] : 0.0;
+                            }
+                    }
                     for (int kk = 0; kk < k4; ++kk) {
                         const int a = kk * 4 + t;
                         const bool live = a < k;
@@ -205,7 +228,7 @@ __global__ void update_kernel(const UpdateParams p, const int ldu, const double 
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int c = tn + nj * 8 + 2 * t + e;
-                                if (c < n) Gb[r + (long long)c * ld] -= acc2[mi][nj][e];
+                                if (c < n) Gb[r + (long long)c * ld] = acc2[mi][nj][e];
                             }
                     }
                 }
@@ -229,7 +252,7 @@ cudaError_t launch_update(const UpdateParams& p, cudaStream_t st)
     int nt = ((p.n + 31) / 32) * 32;
     if (nt < 64) nt = 64;
     if (nt > 1024) nt = 1024;
-    const size_t smem = (size_t)p.nb * 2 * p.kb * ldu * sizeof(double) + sizeof(UpdShared) + (size_t)p.n + 16;
+    const size_t smem = (size_t)p.nb * 2 * p.kb * ldu * sizeof(double) + sizeof(UpdShared) + (size_t)p.n * 9 + 16;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     static size_t configured = 0;
     if (smem > configured) {
