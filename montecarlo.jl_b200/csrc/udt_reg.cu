@@ -101,11 +101,9 @@ __device__ __forceinline__ int col_of_lane(int lane) { return ((lane & 16) ? 4 :
 
 // cluster barrier with release/acquire at cluster scope (cg::cluster_group::sync() adds a
 // GPU-scope MEMBAR in front of the same barrier; DSMEM + cluster-scope ordering is all we need)
-__device__ __forceinline__ void cluster_barrier()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_barrier() { cluster_arrive(); cluster_wait(); }
 
 // dot products of v with the active columns over register rows R0..RPL-1 (v is 0 on rows < j)
 template <int RPL, int R0>
@@ -285,10 +283,7 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
             v[r] = (row < n) ? x : 0.0;
         }
         const unsigned long long m0 = (lane + 32 * r0 > j) ? ~0ull : 0ull;   // rows of register row r0 that are > j
-        if (rank == br && warp == 0) {                   // full Householder vector (0 .. 0 1 v) -> global, for Q
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) Vg[lane + 32 * r + (long long)j * ldv] = v[r];
-        }
+        const bool store_v = (rank == br && warp == 0);  // done after the barrier arrive, see below
         if (tid == 0) {
             const double ad = fabs(rjj);
             dvec[j] = (ad == 0.0) ? 1.0 : ad;
@@ -321,8 +316,15 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
             warp_candidate((j + 1) & 1);
             __syncthreads();
             publish(j + 1);
-            cluster_barrier();
+            cluster_arrive();
         }
+        // the Householder vector (0 .. 0 1 v) goes to global memory (for Q) between arrive and wait so
+        // that the release fence of the barrier never has to wait for these stores
+        if (store_v) {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) Vg[lane + 32 * r + (long long)j * ldv] = v[r];
+        }
+        if (j + 1 < n) cluster_wait();
     }
     __threadfence();
     cluster_barrier();       // V (global) of every step owner is visible cluster-wide; dvec/perm final
