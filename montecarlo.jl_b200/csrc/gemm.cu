@@ -12,6 +12,7 @@
 // staged with a 3-stage cp.async (LDGSTS) ring into padded shared memory laid out
 // so that every fragment load is bank-conflict free (leading dimension = 4 mod 16
 // doubles).  Roofline: FP64 pipe.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dqmc {
@@ -30,14 +31,12 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
 
-constexpr int BK = 16;
-constexpr int STAGES = 3;
-constexpr int KPAD = BK + 4;   // K-major tiles: (x, k) at x * KPAD + k ; 20 = 4 mod 16
+// K-major tiles: (x, k) at x * (BK + 4) + k ; BK + 4 = 4 mod 16 for BK = 16 and 32
 
 // Loads a tile of X (XT x BK in "x,k" terms) into shared memory.
 //  kmajor_global == false : global element (x, k) at g[x + k * ld]  (x contiguous) -> smem (x,k) at k*(XT+4) + x
 //  kmajor_global == true  : global element (x, k) at g[k + x * ld]  (k contiguous) -> smem (x,k) at x*KPAD + k
-template <int XT, bool KMAJOR, int NTHREADS>
+template <int XT, bool KMAJOR, int NTHREADS, int BK>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int ld, int x0, int k0,
                                           int X, int K, int tid)
 {
@@ -59,21 +58,21 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
             int bytes = 0;
             if (gx < X) bytes = (gk + 1 < K) ? 16 : ((gk < K) ? 8 : 0);
             const double* src = bytes ? (g + gk + (long long)gx * ld) : g;
-            cp_async16(s + x * KPAD + k, src, bytes);
+            cp_async16(s + x * (BK + 4) + k, src, bytes);
         }
     }
 }
 
-template <int XT, bool KMAJOR>
+template <int XT, bool KMAJOR, int BK>
 __device__ __forceinline__ double tile_at(const double* s, int x, int k)
 {
     if constexpr (!KMAJOR) return s[k * (XT + 4) + x];
-    else return s[x * KPAD + k];
+    else return s[x * (BK + 4) + k];
 }
 
-template <int XT, bool KMAJOR> __host__ __device__ constexpr int tile_elems() { return KMAJOR ? XT * KPAD : BK * (XT + 4); }
+template <int XT, bool KMAJOR, int BK> __host__ __device__ constexpr int tile_elems() { return KMAJOR ? XT * (BK + 4) : BK * (XT + 4); }
 
-template <int BM, int BN, int WM, int WN, bool TA, bool TB>
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, int BK, int STAGES>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 gemm_kernel(const GemmParams p)
 {
@@ -83,7 +82,7 @@ gemm_kernel(const GemmParams p)
     constexpr bool AK = TA;
     // B tile (n, k): global B is K x N col-major (k contiguous) unless transB
     constexpr bool BKM = !TB;
-    constexpr int AE = tile_elems<BM, AK>(), BE = tile_elems<BN, BKM>();
+    constexpr int AE = tile_elems<BM, AK, BK>(), BE = tile_elems<BN, BKM, BK>();
 
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
@@ -110,8 +109,8 @@ gemm_kernel(const GemmParams p)
 
     auto issue = [&](int stage, int kt) {
         const int k0 = kt * BK;
-        load_tile<BM, AK, NT>(As + stage * AE, A, p.lda, m0, k0, p.M, p.K, tid);
-        load_tile<BN, BKM, NT>(Bs + stage * BE, B, p.ldb, n0, k0, p.N, p.K, tid);
+        load_tile<BM, AK, NT, BK>(As + stage * AE, A, p.lda, m0, k0, p.M, p.K, tid);
+        load_tile<BN, BKM, NT, BK>(Bs + stage * BE, B, p.ldb, n0, k0, p.N, p.K, tid);
         if (has_ks && tid < BK) {
             const int gk = k0 + tid;
             Ks[stage * BK + tid] = (gk < p.K) ? scale_at(p.ks, mat, gk) : 0.0;
@@ -139,9 +138,9 @@ gemm_kernel(const GemmParams p)
             const int k = kk * 4 + t;
             double af[MI], bf[NJ];
 #pragma unroll
-            for (int i = 0; i < MI; ++i) af[i] = tile_at<BM, AK>(as, wm0 + i * 8 + g, k);
+            for (int i = 0; i < MI; ++i) af[i] = tile_at<BM, AK, BK>(as, wm0 + i * 8 + g, k);
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) bf[j] = tile_at<BN, BKM>(bs, wn0 + j * 8 + g, k);
+            for (int j = 0; j < NJ; ++j) bf[j] = tile_at<BN, BKM, BK>(bs, wn0 + j * 8 + g, k);
             if (has_ks) {
                 const double sk = ks[k];
 #pragma unroll
@@ -179,13 +178,13 @@ gemm_kernel(const GemmParams p)
     }
 }
 
-template <int BM, int BN, int WM, int WN, bool TA, bool TB>
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, int BK = 16, int STAGES = 3>
 static cudaError_t launch_cfg(const GemmParams& p, cudaStream_t st)
 {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
-    constexpr int AE = tile_elems<BM, TA>(), BE = tile_elems<BN, !TB>();
+    constexpr int AE = tile_elems<BM, TA, BK>(), BE = tile_elems<BN, !TB, BK>();
     constexpr int smem = (STAGES * (AE + BE) + STAGES * BK) * (int)sizeof(double);
-    auto kern = gemm_kernel<BM, BN, WM, WN, TA, TB>;
+    auto kern = gemm_kernel<BM, BN, WM, WN, TA, TB, BK, STAGES>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -207,7 +206,15 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
         return mm * nn / ((double)p.M * (double)p.N);
     };
     const double w64 = waste(64, 64), w48 = waste(48, 48), w32 = waste(32, 32);
-    if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) return launch_cfg<64, 64, 32, 32, TA, TB>(p, st);
+    static const int variant = getenv("DQMC_GEMM_VARIANT") ? atoi(getenv("DQMC_GEMM_VARIANT")) : 0;
+    if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) {
+        if (variant == 1 && p.M % 128 == 0) return launch_cfg<128, 64, 32, 32, TA, TB>(p, st);
+        if (variant == 2) return launch_cfg<64, 64, 32, 32, TA, TB, 32, 3>(p, st);
+        if (variant == 3) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4>(p, st);
+        if (variant == 4 && p.M % 128 == 0) return launch_cfg<128, 64, 32, 32, TA, TB, 16, 4>(p, st);
+        if (variant == 5) return launch_cfg<64, 64, 32, 16, TA, TB>(p, st);
+        return launch_cfg<64, 64, 32, 32, TA, TB>(p, st);
+    }
     if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
     return launch_cfg<32, 32, 16, 16, TA, TB>(p, st);
 }

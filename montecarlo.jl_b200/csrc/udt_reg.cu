@@ -17,24 +17,28 @@
 //     warp streams the Householder vectors from L2 into registers (prefetched one step ahead).
 // Bound: latency of the per-step critical path (barrier + shuffle trees), then FP64 FMA issue.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace dqmc {
 
-struct UdtRegGeom { int cs, nwarps, nloc, nv, rpl; size_t smem; };
+struct UdtRegGeom { int cs, nwarps, nloc, nv, rpl, skip_q; size_t smem; long long* dbg; };
 
 static bool udt_reg_geometry(int n, UdtRegGeom& g)
 {
     const int rpl = (n + 31) / 32;
     if (rpl > 9) return false;
     const int maxw = (rpl <= 4) ? 16 : ((rpl <= 6) ? 9 : 8);   // matches the __launch_bounds__ below
-    for (int cs = 1; cs <= 8; cs *= 2) {
+    static const int min_cs = getenv("DQMC_UDT_CS") ? atoi(getenv("DQMC_UDT_CS")) : 1;   // experiment knob
+    for (int cs = min_cs; cs <= 8; cs *= 2) {
         const int nloc = (n + cs - 1) / cs;
         const int w = (nloc + 7) / 8;
         if (w <= maxw) {
             g.cs = cs; g.nwarps = w; g.nloc = nloc; g.rpl = rpl; g.nv = rpl * 32;
+            g.dbg = nullptr;
+            g.skip_q = getenv("DQMC_UDT_SKIPQ") ? 1 : 0;   // timing experiments only (results are wrong)
             g.smem = ((size_t)2 * cs * g.nv + 2 * n + 16 + 2 * 32) * sizeof(double) +
                      ((size_t)w * 8 + n + 16 + 2 * 32 + 8) * sizeof(int);
             return true;
@@ -105,50 +109,85 @@ __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void cluster_barrier() { cluster_arrive(); cluster_wait(); }
 
-// dot products of v with the active columns over register rows R0..RPL-1 (v is 0 on rows < j)
-template <int RPL, int R0>
-__device__ __forceinline__ void col_dots(const double (&a)[8][RPL], const double (&v)[RPL], unsigned act, double (&part)[8])
+// dot products of v with all 8 columns over register rows R0..RPL-1 (v is 0 on rows < j).  The 8
+// accumulation chains are interleaved explicitly (r outer, c inner): FP64 FMA has ~10 cycles of
+// dependent latency and ptxas keeps source order under this register pressure.  Inactive columns are
+// computed too and masked afterwards (their dot is forced to 0 so the update leaves them untouched).
+template <int RPL>
+__device__ __forceinline__ void col_dots(const double (&a)[8][RPL], const double (&v)[RPL], unsigned act, double (&part)[8], int r0)
 {
+    double d[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        double d = 0.0;
-        if ((act >> c) & 1u) {
+    for (int c = 0; c < 8; ++c) d[c] = 0.0;
 #pragma unroll
-            for (int r = R0; r < RPL; ++r) d = fma(v[r], a[c][r], d);
+    for (int r = 0; r < RPL; ++r)
+        if (r >= r0) {                                   // warp-uniform branch around 8 independent FMAs
+#pragma unroll
+            for (int c = 0; c < 8; ++c) d[c] = fma(v[r], a[c][r], d[c]);
         }
-        part[c] = d;
-    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) part[c] = ((act >> c) & 1u) ? d[c] : 0.0;
 }
 
-// a[:, c] -= v * (tau * dot_c); part[c] <- sum of squares of the rows > j (only register row R0
+// a[:, c] -= v * (tau * dot_c); part[c] <- sum of squares of the rows > j (only register row r0
 // can contain rows <= j, it is masked with an integer AND instead of FP64 selects)
-template <int RPL, int R0, bool NORMS>
+template <int RPL, bool NORMS>
 __device__ __forceinline__ void col_update(double (&a)[8][RPL], const double (&v)[RPL], unsigned act, double (&part)[8],
-                                           double tau, unsigned long long m0)
+                                           double tau, unsigned long long m0, int r0)
 {
+    double sd[8], nr[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        double nr = 0.0;
-        if ((act >> c) & 1u) {
-            const double sdot = part[c] * tau;
+    for (int c = 0; c < 8; ++c) { sd[c] = part[c] * tau; nr[c] = 0.0; }
 #pragma unroll
-            for (int r = R0; r < RPL; ++r) {
-                const double x = fma(-v[r], sdot, a[c][r]);
+    for (int r = 0; r < RPL; ++r) {
+        if (r > r0) {
+            const double nv = -v[r];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double x = fma(nv, sd[c], a[c][r]);
                 a[c][r] = x;
-                if (NORMS) {
-                    const double xm = (r == R0) ? __longlong_as_double(__double_as_longlong(x) & (long long)m0) : x;
-                    nr = fma(xm, x, nr);
-                }
+                if (NORMS) nr[c] = fma(x, x, nr[c]);
+            }
+        } else if (r == r0) {
+            const double nv = -v[r];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double x = fma(nv, sd[c], a[c][r]);
+                a[c][r] = x;
+                if (NORMS) nr[c] = fma(__longlong_as_double(__double_as_longlong(x) & (long long)m0), x, nr[c]);
             }
         }
-        part[c] = nr;
     }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) part[c] = nr[c];
 }
 
-#define DQMC_R0_CASE(K, BODY) case K: if constexpr (K < RPL) { constexpr int R0 = K; BODY; } break;
-#define DQMC_DISPATCH_R0(r0, BODY) switch (r0) { DQMC_R0_CASE(0, BODY) DQMC_R0_CASE(1, BODY) DQMC_R0_CASE(2, BODY) \
-    DQMC_R0_CASE(3, BODY) DQMC_R0_CASE(4, BODY) DQMC_R0_CASE(5, BODY) DQMC_R0_CASE(6, BODY) DQMC_R0_CASE(7, BODY)    \
-    DQMC_R0_CASE(8, BODY) default: break; }
+// 1/sqrt(x) and sqrt(x) to ~1 ulp: hardware seed (MUFU.RSQ64H) + two coupled Newton steps.  The
+// library sqrt()/division are ~15-deep dependent FP64 chains each; they sit on the critical path
+// of every Householder step.  x must be a positive normal number.
+__device__ __forceinline__ void fast_rsqrt_sqrt(double x, double& rs, double& sq)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double g = x * r, h = 0.5 * r;
+    double e = fma(-g, h, 0.5);
+    g = fma(g, e, g); h = fma(h, e, h);
+    e = fma(-g, h, 0.5);
+    g = fma(g, e, g); h = fma(h, e, h);
+    sq = g; rs = h + h;
+}
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+#define DQMC_TICK(slot) do { if (dbg) { const long long t__ = clock64(); if (tid == 0) dbg[slot] += t__ - tprev; tprev = t__; } } while (0)
 
 template <int RPL>
 __global__ void __launch_bounds__((RPL <= 4) ? 512 : ((RPL <= 6) ? 288 : 256))
@@ -175,6 +214,8 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
     const double* Ag = p.A + (long long)mat * p.strideA;
     double* Vg = p.Vwork + (long long)mat * p.strideV;
     const int ld = p.ld, ldv = p.ldv;
+    long long* dbg = (blockIdx.x == 0) ? gm.dbg : nullptr;   // per-phase cycle counters of CTA 0 (debug)
+    long long tprev = dbg ? clock64() : 0;
 
     // ---- load the panel into registers ------------------------------------------------------
     double a[8][RPL];
@@ -225,23 +266,18 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
         const int s = (bv >= 0.0) ? (bc - rank) / CS : -1;
         if (s >= 0 && (s >> 3) == warp) {                // the warp that owns the winning column
             const int cc = s & 7;
-            double colv[RPL];
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) colv[r] = 0.0;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                if (c == cc) {
+                if (c == cc) {                           // warp-uniform: stores straight from registers
+                    for (int rk = 0; rk < CS; ++rk) {
+                        double* rv = cluster.map_shared_rank(vbuf, rk) + ((size_t)q * CS + rank) * nv;
 #pragma unroll
-                    for (int r = 0; r < RPL; ++r) colv[r] = a[c][r];
+                        for (int r = 0; r < RPL; ++r) {
+                            const int row = lane + 32 * r;
+                            if (row >= j) rv[row] = a[c][r];
+                        }
+                    }
                 }
-            for (int rk = 0; rk < CS; ++rk) {
-                double* rv = cluster.map_shared_rank(vbuf, rk) + ((size_t)q * CS + rank) * nv;
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    const int row = lane + 32 * r;
-                    if (row >= j) rv[row] = colv[r];
-                }
-            }
         }
         if (tid == 0) {
             for (int rk = 0; rk < CS; ++rk) {
@@ -252,13 +288,30 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
     };
 
     cluster_barrier();                                   // peers resident before any DSMEM store
-    warp_candidate(0);
-    __syncthreads();
-    publish(0);
-    cluster_barrier();
 
+    DQMC_TICK(0);
+    double vprev[RPL];                                   // Householder vector of the previous step (stored late)
+    bool store_prev = false;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) vprev[r] = 0.0;
     for (int j = 0; j < n; ++j) {
         const int q = j & 1;
+        // ---- pick and publish this CTA's best remaining column, then ONE cluster barrier ------
+        warp_candidate(q);
+        DQMC_TICK(7);
+        __syncthreads();
+        DQMC_TICK(8);
+        publish(j);
+        DQMC_TICK(9);
+        cluster_arrive();
+        // the previous Householder vector (0 .. 0 1 v) goes to global memory (for Q) between arrive and
+        // wait, so that the release fence of the barrier never has to wait for these stores
+        if (store_prev) {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) Vg[lane + 32 * r + (long long)(j - 1) * ldv] = vprev[r];
+        }
+        cluster_wait();
+        DQMC_TICK(10);
         // ---- global winner, identical in every CTA ------------------------------------------
         double bv = candval[q * 8]; int bc = candcol[q * 8], br = 0;
         for (int r = 1; r < CS; ++r) {
@@ -268,12 +321,21 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
         const double* raw = vbuf + ((size_t)q * CS + br) * nv;
         // ---- reflector (UDT.jl:157-172) ------------------------------------------------------
         double xi1 = raw[j], tau, rjj, inv;
-        if (bv == 0.0) { tau = 0.0; rjj = xi1; inv = 0.0; }
-        else {
-            const double nu = copysign(sqrt(bv), xi1);
-            xi1 += nu;
-            rjj = -nu; tau = xi1 / nu; inv = 1.0 / xi1;
+        if (bv < 1e-290 || bv > 1e290) {                 // exact zero / out of the fast path's range: library math
+            if (bv == 0.0) { tau = 0.0; rjj = xi1; inv = 0.0; }
+            else {
+                const double nu = copysign(sqrt(bv), xi1);
+                xi1 += nu;
+                rjj = -nu; tau = xi1 / nu; inv = 1.0 / xi1;
+            }
+        } else {
+            double rs, sq;
+            fast_rsqrt_sqrt(bv, rs, sq);
+            const double nu = copysign(sq, xi1);
+            xi1 += nu;                                   // |xi1| >= sqrt(bv): never cancels
+            rjj = -nu; tau = xi1 * copysign(rs, nu); inv = fast_rcp(xi1);
         }
+        DQMC_TICK(1);                                    // winner + reflector scalars
         const int r0 = j >> 5;                           // first register row that can be >= j
         double v[RPL];
 #pragma unroll
@@ -296,35 +358,35 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
                 const int cc = s & 7;
                 act &= ~(1u << cc);
                 if (lane == 0) colstep[s] = j;
-                if (lane == (j & 31)) {
-                    DQMC_DISPATCH_R0(r0, {
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) if (c == cc) a[c][R0] = rjj;
-                    })
-                }
+                for (int r = 0; r < RPL; ++r)
+                    if (r == r0) {                       // warp-uniform
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (c == cc && lane == (j & 31)) a[c][r] = rjj;
+                    }
             }
         }
 
+        DQMC_TICK(2);                                    // v, bookkeeping, retire
         // ---- apply H_j to the active columns of this warp, fused norm recompute -------------
         if (act != 0u) {                                 // warp-uniform
-            DQMC_DISPATCH_R0(r0, (col_dots<RPL, R0>(a, v, act, part)))
+            col_dots<RPL>(a, v, act, part, r0);
+            DQMC_TICK(3);
             warp_allreduce8(part, lane);
-            DQMC_DISPATCH_R0(r0, (col_update<RPL, R0, true>(a, v, act, part, tau, m0)))
+            DQMC_TICK(4);
+            col_update<RPL, true>(a, v, act, part, tau, m0, r0);
+            DQMC_TICK(5);
             mynorm = warp_reduce8(part, lane);
+            DQMC_TICK(6);
         }
-        if (j + 1 < n) {
-            warp_candidate((j + 1) & 1);
-            __syncthreads();
-            publish(j + 1);
-            cluster_arrive();
-        }
-        // the Householder vector (0 .. 0 1 v) goes to global memory (for Q) between arrive and wait so
-        // that the release fence of the barrier never has to wait for these stores
-        if (store_v) {
+        store_prev = store_v;
 #pragma unroll
-            for (int r = 0; r < RPL; ++r) Vg[lane + 32 * r + (long long)j * ldv] = v[r];
-        }
-        if (j + 1 < n) cluster_wait();
+        for (int r = 0; r < RPL; ++r) vprev[r] = v[r];
+    }
+    if (store_prev) {
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) Vg[lane + 32 * r + (long long)(n - 1) * ldv] = vprev[r];
     }
     __threadfence();
     cluster_barrier();       // V (global) of every step owner is visible cluster-wide; dvec/perm final
@@ -355,6 +417,7 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
         }
     }
 
+    DQMC_TICK(11);
     // ---- explicit Q, backwards (UDT.jl:272-288); warps are independent from here on --------------
     int cmax = -1;                                       // largest column owned by this warp
 #pragma unroll
@@ -365,7 +428,7 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
 #pragma unroll
         for (int r = 0; r < RPL; ++r) a[c][r] = (s < nloc && lane + 32 * r == col) ? 1.0 : 0.0;
     }
-    if (cmax >= 0) {
+    if (cmax >= 0 && !gm.skip_q) {
         // reflector k only touches columns >= k, so this warp starts at k = cmax
         double vn[RPL];
         auto load_v = [&](int k, double (&dst)[RPL]) {   // V columns are stored complete (0 .. 0 1 v), ldv = 32 * RPL
@@ -387,11 +450,12 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
                 const int s = warp * 8 + c;
                 if (s < nloc && s * CS + rank >= k) m |= 1u << c;
             }
-            DQMC_DISPATCH_R0(r0, (col_dots<RPL, R0>(a, v, m, part)))
+            col_dots<RPL>(a, v, m, part, r0);
             warp_allreduce8(part, lane);
-            DQMC_DISPATCH_R0(r0, (col_update<RPL, R0, false>(a, v, m, part, tau, 0ull)))
+            col_update<RPL, false>(a, v, m, part, tau, 0ull, r0);
         }
     }
+    DQMC_TICK(12);
     {
         double* Ug = p.U + (long long)mat * p.strideU;
 #pragma unroll
@@ -432,17 +496,36 @@ cudaError_t launch_udt_reg(const UdtParams& p, cudaStream_t st)
     if (p.batch <= 0) return cudaSuccess;
     UdtRegGeom g;
     if (!udt_reg_geometry(p.n, g)) return cudaErrorInvalidConfiguration;
-    switch (g.rpl) {
-    case 1: return launch_reg<1>(p, g, st);
-    case 2: return launch_reg<2>(p, g, st);
-    case 3: return launch_reg<3>(p, g, st);
-    case 4: return launch_reg<4>(p, g, st);
-    case 5: return launch_reg<5>(p, g, st);
-    case 6: return launch_reg<6>(p, g, st);
-    case 7: return launch_reg<7>(p, g, st);
-    case 8: return launch_reg<8>(p, g, st);
-    default: return launch_reg<9>(p, g, st);
+    static const bool want_dbg = getenv("DQMC_UDT_DBG") != nullptr;
+    static long long* dbg_buf = nullptr;
+    if (want_dbg) {
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
+        cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), st);
+        g.dbg = dbg_buf;
     }
+    cudaError_t err;
+    switch (g.rpl) {
+    case 1: err = launch_reg<1>(p, g, st); break;
+    case 2: err = launch_reg<2>(p, g, st); break;
+    case 3: err = launch_reg<3>(p, g, st); break;
+    case 4: err = launch_reg<4>(p, g, st); break;
+    case 5: err = launch_reg<5>(p, g, st); break;
+    case 6: err = launch_reg<6>(p, g, st); break;
+    case 7: err = launch_reg<7>(p, g, st); break;
+    case 8: err = launch_reg<8>(p, g, st); break;
+    default: err = launch_reg<9>(p, g, st); break;
+    }
+    if (want_dbg && err == cudaSuccess) {
+        long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        static const char* nm[13] = {"load+first publish", "winner+reflector", "v+retire", "dots", "allreduce8", "update+norms",
+                                     "reduce8", "warp candidate", "syncthreads", "publish", "vstore+cluster wait", "outputs D/T", "form Q"};
+        fprintf(stderr, "[udt dbg n=%d cs=%d] cycles of CTA 0 thread 0:", p.n, g.cs);
+        for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", nm[i], h[i]);
+        fprintf(stderr, "\n");
+    }
+    return err;
 }
 
 }  // namespace dqmc

@@ -59,7 +59,7 @@ struct UpdShared {
     double coef[2][2];
 };
 
-__global__ void update_kernel(const UpdateParams p, const int ldu, const double em2a, const double ep2a)
+__global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const int ldu, const double em2a, const double ep2a)
 {
     extern __shared__ __align__(16) double sm[];
     const int n = p.n, nb = p.nb, kb = p.kb, ld = p.ld;
@@ -90,18 +90,17 @@ __global__ void update_kernel(const UpdateParams p, const int ldu, const double 
         const int kbc = (n - i0 < kb) ? (n - i0) : kb;
         __syncthreads();               // previous flush (global G) and sconf visible
         // ---- stage the kbc columns and rows of G ---------------------------------
-        for (int b = 0; b < nb; ++b) {
+        for (int e = tid; e < nb * kbc * n; e += NT) {
+            const int b = e / (kbc * n), f = e - b * (kbc * n);
             const double* Gb = G + (long long)b * p.strideG;
-            double* ub = Uc + (size_t)b * kb * ldu;
-            double* wb = Wr + (size_t)b * kb * ldu;
-            for (int e = tid; e < kbc * n; e += NT) {
-                const int j = e / n, r = e - j * n;
-                cp_async8(ub + (size_t)j * ldu + r, Gb + r + (long long)(i0 + j) * ld);
-            }
-            for (int e = tid; e < kbc * n; e += NT) {
-                const int c = e / kbc, j = e - c * kbc;
-                cp_async8(wb + (size_t)j * ldu + c, Gb + (i0 + j) + (long long)c * ld);
-            }
+            const int j = f / n, r = f - j * n;
+            cp_async8(Uc + ((size_t)b * kb + j) * ldu + r, Gb + r + (long long)(i0 + j) * ld);
+        }
+        for (int e = tid; e < nb * kbc * n; e += NT) {
+            const int b = e / (kbc * n), f = e - b * (kbc * n);
+            const double* Gb = G + (long long)b * p.strideG;
+            const int c = f / kbc, j = f - c * kbc;
+            cp_async8(Wr + ((size_t)b * kb + j) * ldu + c, Gb + (i0 + j) + (long long)c * ld);
         }
         cp_async_wait_all();
         __syncthreads();
@@ -151,21 +150,20 @@ __global__ void update_kernel(const UpdateParams p, const int ldu, const double 
             const int acc = sh->dec[j & 1];
             if (acc) {
                 // ---- new delayed factors (fields.jl:271-286) ------------------------------
-                for (int b = 0; b < nb; ++b) {
+                for (int e = tid; e < nb * n; e += NT) {
+                    const int b = (e >= n) ? 1 : 0, r = e - b * n;
                     double* ub = Uc + (size_t)b * kb * ldu;
                     double* wb = Wr + (size_t)b * kb * ldu;
                     const double coef = sh->coef[j & 1][b];
-                    for (int r = tid; r < n; r += NT) {
-                        double col = ub[(size_t)j * ldu + r];
-                        double row = wb[(size_t)j * ldu + r];
-                        for (int a = 0; a < k; ++a) {
-                            col += ub[(size_t)a * ldu + r] * wb[(size_t)a * ldu + i];
-                            row += ub[(size_t)a * ldu + i] * wb[(size_t)a * ldu + r];
-                        }
-                        // element (slot k, r) is only ever touched by this thread until the barrier
-                        ub[(size_t)k * ldu + r] = col - ((r == i) ? 1.0 : 0.0);     // -u = G[:, i] - e_i
-                        wb[(size_t)k * ldu + r] = coef * row;
+                    double col = ub[(size_t)j * ldu + r];
+                    double row = wb[(size_t)j * ldu + r];
+                    for (int a = 0; a < k; ++a) {
+                        col += ub[(size_t)a * ldu + r] * wb[(size_t)a * ldu + i];
+                        row += ub[(size_t)a * ldu + i] * wb[(size_t)a * ldu + r];
                     }
+                    // element (slot k, r) is only ever touched by this thread until the barrier
+                    ub[(size_t)k * ldu + r] = col - ((r == i) ? 1.0 : 0.0);     // -u = G[:, i] - e_i
+                    wb[(size_t)k * ldu + r] = coef * row;
                 }
                 // the loop above reads slot-a entries at index i written by other threads in
                 // earlier steps (already separated by barriers) and slot j/k entries of its own r.
@@ -180,11 +178,12 @@ __global__ void update_kernel(const UpdateParams p, const int ldu, const double 
             const int g = lane >> 2, t = lane & 3;
             const int tiles = (n + 31) / 32;
             const int k4 = (k + 3) / 4;
-            for (int b = 0; b < nb; ++b) {
-                double* Gb = G + (long long)b * p.strideG;
-                const double* ub = Uc + (size_t)b * kb * ldu;
-                const double* wb = Wr + (size_t)b * kb * ldu;
-                for (int tile = warp; tile < tiles * tiles; tile += nwarps) {
+            {
+                for (int bt = warp; bt < nb * tiles * tiles; bt += nwarps) {
+                    const int b = bt / (tiles * tiles), tile = bt - b * (tiles * tiles);
+                    double* Gb = G + (long long)b * p.strideG;
+                    const double* ub = Uc + (size_t)b * kb * ldu;
+                    const double* wb = Wr + (size_t)b * kb * ldu;
                     const int tm = (tile % tiles) * 32, tn = (tile / tiles) * 32;
                     // acc <- G tile (all loads in flight together), then acc += (-u) w^T, then store
                     double acc2[4][4][2];
@@ -249,9 +248,9 @@ cudaError_t launch_update(const UpdateParams& p, cudaStream_t st)
 {
     if (p.n_chains <= 0) return cudaSuccess;
     const int ldu = update_ldu(p.n);
-    int nt = ((p.n + 31) / 32) * 32;
+    int nt = ((p.n + 31) / 32) * 32;             // one thread per row (flavor blocks in turn)
     if (nt < 64) nt = 64;
-    if (nt > 1024) nt = 1024;
+    if (nt > 384) nt = 384;
     const size_t smem = (size_t)p.nb * 2 * p.kb * ldu * sizeof(double) + sizeof(UpdShared) + (size_t)p.n * 9 + 16;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     static size_t configured = 0;
