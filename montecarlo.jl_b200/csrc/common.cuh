@@ -49,6 +49,7 @@ struct GemmParams {
     Scale rs, ks, cs;
     const double* add_diag; long long add_stride;
     int batch;
+    int krep;            // 0 / 1 normally; > 1 repeats the k loop (timing experiments only)
 };
 
 cudaError_t launch_gemm(const GemmParams& p, cudaStream_t st);

@@ -33,35 +33,72 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 // K-major tiles: (x, k) at x * (BK + 4) + k ; BK + 4 = 4 mod 16 for BK = 16 and 32
 
-// Loads a tile of X (XT x BK in "x,k" terms) into shared memory.
-//  kmajor_global == false : global element (x, k) at g[x + k * ld]  (x contiguous) -> smem (x,k) at k*(XT+4) + x
-//  kmajor_global == true  : global element (x, k) at g[k + x * ld]  (k contiguous) -> smem (x,k) at x*KPAD + k
+// Per-thread copy descriptors of one operand tile (XT x BK in "x,k" terms), computed ONCE per CTA:
+// every k-tile then costs one pointer bump and NCH cp.async with precomputed offsets (the div/mod
+// address arithmetic per chunk was ~20 % of the main loop).
+//  KMAJOR == false : global element (x, k) at g[x + k * ld]  (x contiguous) -> smem (x,k) at k*(XT+4) + x
+//  KMAJOR == true  : global element (x, k) at g[k + x * ld]  (k contiguous) -> smem (x,k) at x*(BK+4) + k
 template <int XT, bool KMAJOR, int NTHREADS, int BK>
-__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int ld, int x0, int k0,
-                                          int X, int K, int tid)
-{
-    if constexpr (!KMAJOR) {
-        constexpr int CH = XT / 2;                 // 16-byte chunks per k-row
-        for (int c = tid; c < CH * BK; c += NTHREADS) {
-            const int k = c / CH, x = (c - k * CH) * 2;
-            const int gx = x0 + x, gk = k0 + k;
-            int bytes = 0;
-            if (gk < K) bytes = (gx + 1 < X) ? 16 : ((gx < X) ? 8 : 0);
-            const double* src = bytes ? (g + gx + (long long)gk * ld) : g;
-            cp_async16(s + k * (XT + 4) + x, src, bytes);
+struct TileLoader {
+    static constexpr int NCHUNK = XT * BK / 2;                       // 16-byte chunks per tile
+    static constexpr int NCH = (NCHUNK + NTHREADS - 1) / NTHREADS;   // per thread
+    int info[NCH];      // bits 0-4: bytes allowed by the x edge (0 / 8 / 16), bits 8-15: k, bits 16-23: x inside the tile
+    int ld_;
+    const double* g;    // points at (x0, k0) of the current k-tile
+    long long kstep;    // elements to advance per k-tile
+
+    __device__ __forceinline__ void init(const double* base, int ld, int x0, int X, int tid)
+    {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const int c = tid + i * NTHREADS;
+            int x, k, xb;
+            if constexpr (!KMAJOR) {
+                constexpr int CH = XT / 2;
+                k = c / CH; x = (c - k * CH) * 2;
+                xb = (x0 + x + 1 < X) ? 16 : ((x0 + x < X) ? 8 : 0);
+            } else {
+                constexpr int CH = BK / 2;
+                x = c / CH; k = (c - x * CH) * 2;
+                xb = (x0 + x < X) ? 16 : 0;
+            }
+            if (c >= NCHUNK) { xb = 0; x = 0; k = 0; }
+            info[i] = xb | (k << 8) | (x << 16);
         }
-    } else {
-        constexpr int CH = BK / 2;
-        for (int c = tid; c < CH * XT; c += NTHREADS) {
-            const int x = c / CH, k = (c - x * CH) * 2;
-            const int gx = x0 + x, gk = k0 + k;
-            int bytes = 0;
-            if (gx < X) bytes = (gk + 1 < K) ? 16 : ((gk < K) ? 8 : 0);
-            const double* src = bytes ? (g + gk + (long long)gx * ld) : g;
-            cp_async16(s + x * (BK + 4) + k, src, bytes);
+        ld_ = ld;
+        if constexpr (!KMAJOR) { g = base + x0; kstep = (long long)BK * ld; }
+        else { g = base + (long long)x0 * ld; kstep = BK; }
+    }
+
+    // issue the copies of the k-tile `g` currently points at; krem = K - k0 (> 0)
+    __device__ __forceinline__ void issue(double* s, int krem, int tid)
+    {
+        if (krem >= BK) {
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                if (NCHUNK % NTHREADS != 0 && tid + i * NTHREADS >= NCHUNK) continue;
+                const int xb = info[i] & 31, k = (info[i] >> 8) & 255, x = info[i] >> 16;
+                const int so = KMAJOR ? (k + x * ld_) : (x + k * ld_);
+                const int dof = KMAJOR ? (x * (BK + 4) + k) : (k * (XT + 4) + x);
+                cp_async16(s + dof, xb ? (g + so) : g, xb);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                if (NCHUNK % NTHREADS != 0 && tid + i * NTHREADS >= NCHUNK) continue;
+                const int xb = info[i] & 31, k = (info[i] >> 8) & 255, x = info[i] >> 16;
+                const int so = KMAJOR ? (k + x * ld_) : (x + k * ld_);
+                const int dof = KMAJOR ? (x * (BK + 4) + k) : (k * (XT + 4) + x);
+                int bytes;
+                if constexpr (!KMAJOR) bytes = (k < krem) ? xb : 0;
+                else bytes = xb ? ((k + 1 < krem) ? 16 : ((k < krem) ? 8 : 0)) : 0;
+                cp_async16(s + dof, bytes ? (g + so) : g, bytes);
+            }
         }
     }
-}
+    __device__ __forceinline__ void advance() { g += kstep; }
+    __device__ __forceinline__ void rewind(int ktiles) { g -= kstep * ktiles; }
+};
 
 template <int XT, bool KMAJOR, int BK>
 __device__ __forceinline__ double tile_at(const double* s, int x, int k)
@@ -72,8 +109,8 @@ __device__ __forceinline__ double tile_at(const double* s, int x, int k)
 
 template <int XT, bool KMAJOR, int BK> __host__ __device__ constexpr int tile_elems() { return KMAJOR ? XT * (BK + 4) : BK * (XT + 4); }
 
-template <int BM, int BN, int WM, int WN, bool TA, bool TB, int BK, int STAGES>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, int BK, int STAGES, int MINB>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
 gemm_kernel(const GemmParams p)
 {
     constexpr int NWM = BM / WM, NWN = BN / WN, NT = NWM * NWN * 32;
@@ -92,12 +129,17 @@ gemm_kernel(const GemmParams p)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int wm0 = (warp % NWM) * WM, wn0 = (warp / NWM) * WN;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, mat = blockIdx.z;
+    const bool has_ks = p.ks.mode != 0;
+    const bool has_rs = p.rs.mode != 0, has_cs = p.cs.mode != 0;
 
+    // one CTA per output tile (a persistent variant with a cross-tile cp.async ring was measured
+    // slower: 25.8 vs 26.8 TFLOP/s at K = 256 -- the block scheduler already staggers the 8 waves)
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, mat = blockIdx.z;
     const double* A = p.A + (long long)mat * p.strideA;
     const double* B = p.B + (long long)mat * p.strideB;
     double* C = p.C + (long long)mat * p.strideC;
-    const bool has_ks = p.ks.mode != 0;
+    const int KTr = (p.K + BK - 1) / BK;
+    const int KT = KTr * (p.krep > 0 ? p.krep : 1);   // krep > 1: timing experiment only (repeats the k loop)
 
     double acc[MI][NJ][2];
 #pragma unroll
@@ -105,34 +147,41 @@ gemm_kernel(const GemmParams p)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    const int KT = (p.K + BK - 1) / BK;
-
-    auto issue = [&](int stage, int kt) {
-        const int k0 = kt * BK;
-        load_tile<BM, AK, NT, BK>(As + stage * AE, A, p.lda, m0, k0, p.M, p.K, tid);
-        load_tile<BN, BKM, NT, BK>(Bs + stage * BE, B, p.ldb, n0, k0, p.N, p.K, tid);
+    TileLoader<BM, AK, NT, BK> la;
+    TileLoader<BN, BKM, NT, BK> lb;
+    la.init(A, p.lda, m0, p.M, tid);
+    lb.init(B, p.ldb, n0, p.N, tid);
+    int kr_i = 0;                            // k-tile (mod KTr) the loaders point at
+    auto issue = [&](int stage) {
+        const int k0 = kr_i * BK;
+        la.issue(As + stage * AE, p.K - k0, tid);
+        lb.issue(Bs + stage * BE, p.K - k0, tid);
+        la.advance(); lb.advance();
         if (has_ks && tid < BK) {
             const int gk = k0 + tid;
             Ks[stage * BK + tid] = (gk < p.K) ? scale_at(p.ks, mat, gk) : 0.0;
         }
+        if (++kr_i == KTr) { kr_i = 0; la.rewind(KTr); lb.rewind(KTr); }
     };
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT) issue(s, s);
+        if (s < KT) issue(s);
         cp_async_commit();
     }
 
+    int stage = 0, stage_n = STAGES - 1;     // stage being computed / stage the next issue goes to
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        const int nxt = kt + STAGES - 1;
-        if (nxt < KT) issue(nxt % STAGES, nxt);
+        if (kt + STAGES - 1 < KT) issue(stage_n);
         cp_async_commit();
+        if (++stage_n == STAGES) stage_n = 0;
 
-        const double* as = As + (kt % STAGES) * AE;
-        const double* bs = Bs + (kt % STAGES) * BE;
-        const double* ks = Ks + (kt % STAGES) * BK;
+        const double* as = As + stage * AE;
+        const double* bs = Bs + stage * BE;
+        const double* ks = Ks + stage * BK;
+        if (++stage == STAGES) stage = 0;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
             const int k = kk * 4 + t;
@@ -154,8 +203,7 @@ gemm_kernel(const GemmParams p)
     }
     cp_async_wait<0>();
 
-    // epilogue: thread owns C[row = g, cols = 2t, 2t+1] of every 8x8 tile
-    const bool has_rs = p.rs.mode != 0, has_cs = p.cs.mode != 0;
+    // epilogue: thread owns C[row = g, cols = 2t, 2t+1] of every 8x8 block
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
         const int row = m0 + wm0 + i * 8 + g;
@@ -178,13 +226,13 @@ gemm_kernel(const GemmParams p)
     }
 }
 
-template <int BM, int BN, int WM, int WN, bool TA, bool TB, int BK = 16, int STAGES = 3>
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, int BK = 16, int STAGES = 3, int MINB = 4>
 static cudaError_t launch_cfg(const GemmParams& p, cudaStream_t st)
 {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int AE = tile_elems<BM, TA, BK>(), BE = tile_elems<BN, !TB, BK>();
     constexpr int smem = (STAGES * (AE + BE) + STAGES * BK) * (int)sizeof(double);
-    auto kern = gemm_kernel<BM, BN, WM, WN, TA, TB, BK, STAGES>;
+    auto kern = gemm_kernel<BM, BN, WM, WN, TA, TB, BK, STAGES, MINB>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -208,20 +256,37 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
     const double w64 = waste(64, 64), w48 = waste(48, 48), w32 = waste(32, 32);
     static const int variant = getenv("DQMC_GEMM_VARIANT") ? atoi(getenv("DQMC_GEMM_VARIANT")) : 0;
     if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) {
-        if (variant == 1 && p.M % 128 == 0) return launch_cfg<128, 64, 32, 32, TA, TB>(p, st);
-        if (variant == 2) return launch_cfg<64, 64, 32, 32, TA, TB, 32, 3>(p, st);
-        if (variant == 3) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4>(p, st);
-        if (variant == 4 && p.M % 128 == 0) return launch_cfg<128, 64, 32, 32, TA, TB, 16, 4>(p, st);
-        if (variant == 5) return launch_cfg<64, 64, 32, 16, TA, TB>(p, st);
-        return launch_cfg<64, 64, 32, 32, TA, TB>(p, st);
+        if (variant == 1 && p.M % 128 == 0) return launch_cfg<128, 64, 32, 32, TA, TB, 16, 3, 2>(p, st);
+        if (variant == 2) return launch_cfg<64, 64, 32, 32, TA, TB, 32, 3, 2>(p, st);
+        if (variant == 3) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4, 3>(p, st);
+        if (variant == 4 && p.M % 128 == 0) return launch_cfg<128, 64, 32, 32, TA, TB, 16, 4, 2>(p, st);
+        if (variant == 5) return launch_cfg<64, 64, 32, 16, TA, TB, 16, 3, 2>(p, st);
+        if (variant == 6) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 5>(p, st);
+        if (variant == 7) return launch_cfg<64, 64, 32, 16, TA, TB, 16, 2, 3>(p, st);
+        if (variant == 8) return launch_cfg<64, 64, 16, 32, TA, TB, 16, 3, 2>(p, st);
+        if (variant == 9) return launch_cfg<64, 64, 32, 16, TA, TB, 8, 4, 2>(p, st);
+        if (variant == 10) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 6>(p, st);
+        if (variant == 11) return launch_cfg<64, 64, 32, 32, TA, TB, 8, 3, 5>(p, st);
+        if (variant == 12) return launch_cfg<64, 64, 32, 32, TA, TB, 8, 4, 5>(p, st);
+        if (variant == 13) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 3, 4>(p, st);
+        return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 5>(p, st);   // 2 stages, 5 CTAs/SM: best measured (28.7 TFLOP/s)
     }
     if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
     return launch_cfg<32, 32, 16, 16, TA, TB>(p, st);
 }
 
+static cudaError_t launch_gemm_impl(const GemmParams& p, cudaStream_t st);
+
 cudaError_t launch_gemm(const GemmParams& p, cudaStream_t st)
 {
     if (p.batch <= 0 || p.M <= 0 || p.N <= 0) return cudaSuccess;
+    static const int krep = getenv("DQMC_GEMM_KREP") ? atoi(getenv("DQMC_GEMM_KREP")) : 0;
+    if (krep > 0) { GemmParams q = p; q.krep = krep; return launch_gemm_impl(q, st); }
+    return launch_gemm_impl(p, st);
+}
+
+static cudaError_t launch_gemm_impl(const GemmParams& p, cudaStream_t st)
+{
     if ((p.lda & 1) || (p.ldb & 1)) return cudaErrorInvalidValue;   // 16-byte cp.async columns
     if (!p.transA && !p.transB) return launch_tiles<false, false>(p, st);
     if (!p.transA && p.transB) return launch_tiles<false, true>(p, st);

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "../../include/dqmc_rng.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace dqmc {
 
@@ -59,12 +60,17 @@ struct UpdShared {
     double coef[2][2];
 };
 
-__global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const int ldu, const double em2a, const double ep2a)
+#define UPD_TICK(slot) do { if (dbg) { const long long t__ = clock64(); if (tid == 0) dbg[slot] += t__ - tprev; tprev = t__; } } while (0)
+
+__global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const int ldu, const double em2a, const double ep2a,
+                                                      long long* dbg_all)
 {
     extern __shared__ __align__(16) double sm[];
     const int n = p.n, nb = p.nb, kb = p.kb, ld = p.ld;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
     const int chain = blockIdx.x;
+    long long* dbg = (blockIdx.x == 0) ? dbg_all : nullptr;
+    long long tprev = dbg ? clock64() : 0;
 
     double* Uc = sm;                                   // [nb][kb][ldu]   columns of G0 -> u_a
     double* Wr = Uc + (size_t)nb * kb * ldu;           // [nb][kb][ldu]   rows of G0    -> w_a
@@ -102,8 +108,10 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
             const int c = f / kbc, j = f - c * kbc;
             cp_async8(Wr + ((size_t)b * kb + j) * ldu + c, Gb + (i0 + j) + (long long)c * ld);
         }
+        UPD_TICK(0);
         cp_async_wait_all();
         __syncthreads();
+        UPD_TICK(1);
 
         int k = 0;                     // accepted flips in this block (delayed factors in slots 0..k-1)
         for (int j = 0; j < kbc; ++j) {
@@ -146,7 +154,9 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
                     if (acc) { sconf[i] = (int8_t)(-sconf[i]); conf[i] = sconf[i]; }
                 }
             }
+            if (warp == 0) UPD_TICK(2);
             __syncthreads();
+            UPD_TICK(3);
             const int acc = sh->dec[j & 1];
             if (acc) {
                 // ---- new delayed factors (fields.jl:271-286) ------------------------------
@@ -169,10 +179,13 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
                 // earlier steps (already separated by barriers) and slot j/k entries of its own r.
                 // BUT when k < j another thread's read of ub[k][i] (a < k only) never hits slot k. ok
                 ++k; ++accepted;
+                UPD_TICK(4);
                 __syncthreads();
+                UPD_TICK(5);
             }
         }
 
+        UPD_TICK(6);
         // ---- flush: G_b -= sum_{a<k} u_a w_a^T  (rank-k DMMA update) ---------------------
         if (k > 0) {
             const int g = lane >> 2, t = lane & 3;
@@ -235,6 +248,7 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
         }
     }
 
+    UPD_TICK(7);
     if (tid == 0) {
         if (p.accepted) p.accepted[chain] += accepted;
         if (p.stats && neg_cnt > 0.0) {
@@ -260,9 +274,26 @@ cudaError_t launch_update(const UpdateParams& p, cudaStream_t st)
         configured = smem;
     }
     const double em2a = exp(-2.0 * p.alpha), ep2a = exp(2.0 * p.alpha);
-    update_kernel<<<(unsigned)p.n_chains, nt, smem, st>>>(p, ldu, em2a, ep2a);
+    static const bool want_dbg = getenv("DQMC_UPD_DBG") != nullptr;
+    static long long* dbg_buf = nullptr;
+    if (want_dbg) {
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
+        cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), st);
+    }
+    update_kernel<<<(unsigned)p.n_chains, nt, smem, st>>>(p, ldu, em2a, ep2a, want_dbg ? dbg_buf : nullptr);
     ++g_kernel_launches;
-    return cudaGetLastError();
+    cudaError_t err = cudaGetLastError();
+    if (want_dbg && err == cudaSuccess) {
+        long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        static const char* nm[8] = {"sync+issue staging", "staging wait", "decision(warp0)", "wait decision", "accept update", "sync after accept",
+                                    "flush(prev)+loop", "tail"};
+        fprintf(stderr, "[upd dbg n=%d kb=%d] cycles of CTA 0 thread 0:", p.n, p.kb);
+        for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%lld", nm[i], h[i]);
+        fprintf(stderr, "\n");
+    }
+    return err;
 }
 
 }  // namespace dqmc
