@@ -195,6 +195,7 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
 {
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = gm.cs, nv = gm.nv, n = p.n;
+    const int csh = 31 - __clz(CS);                     // CS is 1, 2, 4 or 8
     const int rank = (int)cluster.block_rank();
     const int mat = blockIdx.x / CS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = gm.nwarps;
@@ -263,7 +264,7 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
             const double ov = wbval[q * 32 + w]; const int oc = wbcol[q * 32 + w];
             if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
         }
-        const int s = (bv >= 0.0) ? (bc - rank) / CS : -1;
+        const int s = (bv >= 0.0) ? ((bc - rank) >> csh) : -1;
         if (s >= 0 && (s >> 3) == warp) {                // the warp that owns the winning column
             const int cc = s & 7;
 #pragma unroll
@@ -353,7 +354,7 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
             perm[j] = bc;
         }
         if (rank == br) {
-            const int s = (bc - rank) / CS;
+            const int s = (bc - rank) >> csh;
             if ((s >> 3) == warp) {                      // retire the pivot column, store R_jj
                 const int cc = s & 7;
                 act &= ~(1u << cc);

@@ -216,7 +216,11 @@ def test_measured_greens(b200):
 
 
 # ===================================================================== the sweep
-def check_sweeps(ctx, chains, nsweeps, gtol=GTOL):
+def check_sweeps(ctx, chains, nsweeps, gtol=GTOL, ptol=1e-7):
+    """ptol: tolerance on the acceptance probabilities *between* stabilisations.  G is only 1e-10-exact
+    right after a stabilisation; in between, wraps amplify round-off (the reference itself reports
+    propagation errors of 1e-7..1e-6 as normal, docs/src/examples/ALF1.md:103-104), so long-beta cases
+    compare p at that scale.  Decisions must still be identical."""
     ctx.build_stack()
     for c in chains:
         c.init()
@@ -231,7 +235,7 @@ def check_sweeps(ctx, chains, nsweeps, gtol=GTOL):
                 u = uniforms_for_sweep(c_seed(ctx, c), b, s, 2 * ctx.M, ctx.N)[st, si]
                 raise AssertionError(f"decision mismatch chain {b} sweep {s} step {st} site {si}: "
                                      f"p_gpu={probs[b, st, si]!r} p_ref={po[st, si]!r} u={u!r}")
-            assert np.allclose(probs[b], po, rtol=1e-7, atol=1e-12)
+            assert np.allclose(probs[b], po, rtol=ptol, atol=1e-12), np.abs(probs[b] / po - 1).max()
             assert a == acc[b]
             assert np.array_equal(conf[:, :, b], c.get_conf())
             assert relerr(G[:, :, :, b], c.greens) < gtol
@@ -411,3 +415,36 @@ def test_observable_accumulators(b200):
     Gm = ctx.measured_greens()
     assert s.shape == (16, 16, 2) and np.all(s2 >= 0)
     assert np.abs(s).max() > 0 and np.isfinite(Gm).all()
+
+
+# ===================================================================== long imaginary time
+@pytest.mark.parametrize("U", [4.0, -4.0])
+def test_sweep_parity_8x8_long_beta(b200, U):
+    """config 2 geometry (8x8, attractive, beta = 10) and its repulsive sibling at beta = 8: D spans
+    ~40 orders of magnitude, every stabilisation matters.  Decisions identical, G <= 1e-10 at sweep end,
+    and the propagation-error statistics (stack.jl:644-654) agree with the oracle's."""
+    beta = 10.0 if U > 0 else 8.0
+    ctx, chains = make_pair(b200, "square", (8, 8), U=U, beta=beta, B=2, seed=5)
+    check_sweeps(ctx, chains, 1, ptol=2e-5)
+    st = ctx.stats()
+    for b, c in enumerate(chains):
+        assert st[b]["prop_count"] == c.stats["prop_count"]
+        if c.stats["prop_count"]:
+            assert np.isclose(st[b]["prop_max"], c.stats["prop_max"], rtol=0.5)
+
+
+def test_honeycomb_L4_sweep(b200):
+    """config 5 family (honeycomb, attractive): N = 32 sites, two-site basis ordering."""
+    ctx, chains = make_pair(b200, "honeycomb", (4, 4), U=4.0, beta=2.0, B=2)
+    check_sweeps(ctx, chains, 2)
+
+
+def test_check_propagation_error_off_is_identical(b200):
+    """parameters.check_propagation_error = false only skips the check (stack.jl:636-654)."""
+    out = []
+    for chk in (True, False):
+        ctx, _ = make_pair(b200, "square", (4, 4), U=-4.0, beta=2.0, B=2, check_prop=chk)
+        ctx.build_stack()
+        acc, p, d = ctx.sweep_traced()
+        out.append((d, ctx.greens()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
