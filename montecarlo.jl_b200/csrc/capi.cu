@@ -39,8 +39,8 @@ struct dqmc_ctx {
     double *u_stack = nullptr, *d_stack = nullptr, *t_stack = nullptr;
     double *greens = nullptr, *greens_temp = nullptr, *Ul = nullptr, *Ur = nullptr, *Tl = nullptr, *Tr = nullptr;
     double *tmp1 = nullptr, *tmp2 = nullptr, *curr_U = nullptr, *Dl = nullptr, *Dr = nullptr;
-    double *Vwork = nullptr, *tau = nullptr;
-    int* pivot = nullptr;
+    double *Vwork = nullptr, *tau = nullptr, *udt_scratch = nullptr;
+    int* pivot = nullptr; int* udt_iscratch = nullptr;
     int* accepted = nullptr;
     double *stats_neg = nullptr, *stats_prop = nullptr;
     double* obs = nullptr; long long obs_len = 0;
@@ -186,6 +186,7 @@ static cudaError_t udt(dqmc_ctx* c, const double* A, Scale colscale, double* U, 
     p.U = U; p.strideU = c->ms; p.D = D; p.strideD = c->N; p.T = T; p.strideT = c->ms;
     p.pivot = c->pivot; p.stridePivot = c->N; p.pivot_applied = apply_pivot ? 1 : 0;
     p.Vwork = c->Vwork; p.ldv = c->ldv; p.strideV = (long long)c->ldv * c->N; p.tau = c->tau; p.strideTau = c->N;
+    p.scratch = c->udt_scratch; p.iscratch = c->udt_iscratch;
     return launch_udt(p, c->st);
 }
 
@@ -482,6 +483,8 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     A_(greens, mat); A_(greens_temp, mat); A_(Ul, mat); A_(Ur, mat); A_(Tl, mat); A_(Tr, mat);
     A_(tmp1, mat); A_(tmp2, mat); A_(curr_U, mat); A_(Vwork, (size_t)c->nmat * c->ldv * c->N);
     A_(Dl, vec); A_(Dr, vec); A_(tau, vec);
+    A_(udt_scratch, (size_t)c->nmat * udt_reg_scratch_doubles(c->N, c->ld));
+    A_(udt_iscratch, (size_t)c->nmat * udt_reg_scratch_ints(c->N));
     A_(pivot, vec); A_(accepted, (size_t)c->B);
     A_(stats_neg, (size_t)c->B * 4); A_(stats_prop, (size_t)c->B * 4);
     c->obs_len = 1 + 2 * (long long)c->nb * c->ms;
@@ -868,6 +871,8 @@ static int32_t make_op_ctx(int device, int n, int batch, dqmc_ctx** out)
     if (e == cudaSuccess) e = dalloc(c, &c->Dr, vec);
     if (e == cudaSuccess) e = dalloc(c, &c->tau, vec);
     if (e == cudaSuccess) e = dalloc(c, &c->pivot, vec);
+    if (e == cudaSuccess) e = dalloc(c, &c->udt_scratch, (size_t)c->nmat * udt_reg_scratch_doubles(n, c->ld));
+    if (e == cudaSuccess) e = dalloc(c, &c->udt_iscratch, (size_t)c->nmat * udt_reg_scratch_ints(n));
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); dqmc_destroy(c); return DQMC_ERR_CUDA; }
     *out = c;
     return DQMC_OK;

@@ -65,8 +65,12 @@ struct UdtParams {
     int* pivot; long long stridePivot;       // logical column j came from input column pivot[j] (0-based)
     int pivot_applied;
     double* Vwork; long long strideV; int ldv; // n columns x ldv (>= 32 * ceil(n/32)) scratch per matrix (Householder vectors)
-    double* tau; long long strideTau;        // n scratch per matrix
+    double* tau; long long strideTau;        // n scratch per matrix (Householder taus)
+    double* scratch;                         // batch * udt_reg_scratch_doubles(n, ld) doubles (multi-level QR)
+    int* iscratch;                           // batch * udt_reg_scratch_ints(n) ints
 };
+size_t udt_reg_scratch_doubles(int n, int ld);
+size_t udt_reg_scratch_ints(int n);
 cudaError_t launch_udt(const UdtParams& p, cudaStream_t st);
 int udt_max_n();
 

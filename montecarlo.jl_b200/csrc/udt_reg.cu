@@ -1,21 +1,32 @@
-// udt_reg.cu -- register-resident batched column-pivoted Householder QR -> UDT (v2 of udt.cu).
+// udt_reg.cu -- register-resident, multi-level batched column-pivoted Householder QR -> UDT.
 //
-// Same mathematics and outputs as udt.cu (reference src/flavors/DQMC/linalg/UDT.jl:216-334),
-// different residence: the n x n/CS column panel of a CTA lives in REGISTERS.
+// Same mathematics and outputs as the reference's udt_AVX_pivot! (src/flavors/DQMC/linalg/UDT.jl:216-334:
+// indmaxcolumn :175-192, reflector! :157-172, reflectorApply! :53-70, Q accumulation :272-288,
+// D = |diag R| with 0 -> 1 :293-301, T = D^-1 R P^T or the unpivoted upper triangle :311-334).
+//
+// Residence.  The n x n/CS column panel of a CTA lives in REGISTERS:
 //   * cluster of CS CTAs per matrix, columns dealt cyclically (column c -> CTA c % CS),
 //   * inside a CTA warp w owns 8 consecutive local columns, lane l owns rows l, l+32, ...
 //     => thread holds a[8][RPL] doubles, RPL = ceil(n/32) (n = 256: 64 doubles = 128 registers),
-//   * per Householder step every lane needs only its RPL entries of v (one conflict-free
-//     shared-memory read each), the 8 column dot products are reduced with a
-//     recursive-halving shuffle tree (17 64-bit shuffles instead of 8 x 5 butterflies),
-//   * the squared norms of the remaining columns are recomputed in the same pass
-//     (UDT.jl:175-192 recomputes them every step as well),
-//   * ONE cluster barrier per step: each CTA publishes its best remaining column (norm, index,
-//     column tail) into every peer's shared memory through DSMEM; after the barrier every CTA
-//     builds the identical reflector redundantly.  Columns are never swapped (free un-pivoting).
-//   * forming Q (UDT.jl:272-288) runs backwards with NO block-level synchronisation at all: each
-//     warp streams the Householder vectors from L2 into registers (prefetched one step ahead).
-// Bound: latency of the per-step critical path (barrier + shuffle trees), then FP64 FMA issue.
+//   * per Householder step every lane needs only its RPL entries of v, the 8 column dot products are
+//     reduced with a recursive-halving shuffle tree, the squared norms of the remaining columns are
+//     recomputed in the same pass (the reference recomputes them every step as well),
+//   * ONE cluster barrier per step: each CTA publishes its best remaining column (norm, index, column
+//     tail) into every peer's shared memory through DSMEM; every CTA then builds the identical
+//     reflector redundantly.  Columns are never swapped (un-pivoting is free).
+//
+// Levels.  A step costs ~3 us of latency (barrier, selection, shuffle trees) whatever the size of the
+// trailing matrix, and a 512 KB matrix needs 4 SMs, so only 33 of the 296 matrices of a cfg-4 launch
+// are in flight.  The factorisation is therefore cut into levels: level 0 does steps 0 .. n/2 on the
+// cluster, writes the rows of R it has finished and exports the (compacted) trailing block; level 1
+// factors that (n/2) x (n/2) block -- which fits ONE SM, so 148 matrices are in flight and there is no
+// cluster barrier -- and so on down to 64 columns.  Every level recomputes the column norms from
+// scratch (as the reference does at every step), so the arithmetic is unchanged.
+//
+// Q.  Formed by a separate full-grid kernel, backwards (UDT.jl:272-288), with NO block-level
+// synchronisation: each warp streams the Householder vectors from L2 into registers one step ahead.
+//
+// Bound: latency of the per-step critical path; FP64 FMA pipe ~13 % busy (profiles/r1_summary.md).
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -24,9 +35,22 @@ namespace cg = cooperative_groups;
 
 namespace dqmc {
 
-struct UdtRegGeom { int cs, nwarps, nloc, nv, rpl, skip_q; size_t smem; long long* dbg; };
+struct UdtLevel {
+    // geometry
+    int cs, nwarps, nloc, nv, rpl; size_t smem;
+    // problem
+    int n;          // size of this level's (sub)matrix
+    int jstop;      // Householder steps done at this level (== n at the last level)
+    int joff;       // steps done by the previous levels == row/step offset of all outputs
+    int ld;         // leading dimension of the input
+    const double* A; long long strideA;          // level 0: the caller's matrix; level > 0: trailing block
+    const int* cmap; long long strideCmap;       // physical column of local column k (nullptr: identity)
+    double* S; int ldS; long long strideS;       // trailing block out ((n - jstop)^2), if jstop < n
+    int* cmap_out; long long strideCmapOut;
+    double* Tphys; long long strideTp;           // T in physical column order (ld = p.ld)
+};
 
-static bool udt_reg_geometry(int n, UdtRegGeom& g)
+static bool udt_level_geometry(int n, UdtLevel& g)
 {
     const int rpl = (n + 31) / 32;
     if (rpl > 9) return false;
@@ -37,8 +61,6 @@ static bool udt_reg_geometry(int n, UdtRegGeom& g)
         const int w = (nloc + 7) / 8;
         if (w <= maxw) {
             g.cs = cs; g.nwarps = w; g.nloc = nloc; g.rpl = rpl; g.nv = rpl * 32;
-            g.dbg = nullptr;
-            g.skip_q = getenv("DQMC_UDT_SKIPQ") ? 1 : 0;   // timing experiments only (results are wrong)
             g.smem = ((size_t)2 * cs * g.nv + 2 * n + 16 + 2 * 32) * sizeof(double) +
                      ((size_t)w * 8 + n + 16 + 2 * 32 + 8) * sizeof(int);
             return true;
@@ -51,7 +73,7 @@ static bool udt_reg_geometry(int n, UdtRegGeom& g)
 __device__ __forceinline__ void warp_allreduce8(double (&x)[8], int lane)
 {
     // recursive halving: after the three exchange rounds lane holds the partial of column
-    // ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1) summed over 8 lanes' worth of data
+    // 4*bit4 + 2*bit3 + bit2 of its lane id, summed over 8 lanes' worth of data
     const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
     double y[4];
 #pragma unroll
@@ -70,7 +92,6 @@ __device__ __forceinline__ void warp_allreduce8(double (&x)[8], int lane)
     double w = (h4 ? z[1] : z[0]) + __shfl_xor_sync(0xffffffffu, h4 ? z[0] : z[1], 4);
     w += __shfl_xor_sync(0xffffffffu, w, 2);
     w += __shfl_xor_sync(0xffffffffu, w, 1);
-    // lane now holds the total of column cidx = 4*h16 + 2*h8 + h4 ; gather all eight
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const int src = ((c & 4) ? 16 : 0) | ((c & 2) ? 8 : 0) | ((c & 1) ? 4 : 0);
@@ -103,13 +124,13 @@ __device__ __forceinline__ double warp_reduce8(const double (&x)[8], int lane)
 }
 __device__ __forceinline__ int col_of_lane(int lane) { return ((lane & 16) ? 4 : 0) | ((lane & 8) ? 2 : 0) | ((lane & 4) ? 1 : 0); }
 
-// cluster barrier with release/acquire at cluster scope (cg::cluster_group::sync() adds a
-// GPU-scope MEMBAR in front of the same barrier; DSMEM + cluster-scope ordering is all we need)
+// cluster barrier with release/acquire at cluster scope (cg::cluster_group::sync() adds a GPU-scope
+// MEMBAR in front of the same barrier; DSMEM + cluster-scope ordering is all we need)
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void cluster_barrier() { cluster_arrive(); cluster_wait(); }
 
-// dot products of v with all 8 columns over register rows R0..RPL-1 (v is 0 on rows < j).  The 8
+// dot products of v with all 8 columns over register rows r0..RPL-1 (v is 0 on rows < j).  The 8
 // accumulation chains are interleaved explicitly (r outer, c inner): FP64 FMA has ~10 cycles of
 // dependent latency and ptxas keeps source order under this register pressure.  Inactive columns are
 // computed too and masked afterwards (their dot is forced to 0 so the update leaves them untouched).
@@ -132,7 +153,7 @@ __device__ __forceinline__ void col_dots(const double (&a)[8][RPL], const double
 // a[:, c] -= v * (tau * dot_c); part[c] <- sum of squares of the rows > j (only register row r0
 // can contain rows <= j, it is masked with an integer AND instead of FP64 selects)
 template <int RPL, bool NORMS>
-__device__ __forceinline__ void col_update(double (&a)[8][RPL], const double (&v)[RPL], unsigned act, double (&part)[8],
+__device__ __forceinline__ void col_update(double (&a)[8][RPL], const double (&v)[RPL], double (&part)[8],
                                            double tau, unsigned long long m0, int r0)
 {
     double sd[8], nr[8];
@@ -187,18 +208,19 @@ __device__ __forceinline__ double fast_rcp(double x)
     return r;
 }
 
-#define DQMC_TICK(slot) do { if (dbg) { const long long t__ = clock64(); if (tid == 0) dbg[slot] += t__ - tprev; tprev = t__; } } while (0)
-
+// ================================================================================================
+// QR steps [0, jstop) of one level
+// ================================================================================================
 template <int RPL>
 __global__ void __launch_bounds__((RPL <= 4) ? 512 : ((RPL <= 6) ? 288 : 256))
-udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
+udt_steps_kernel(const UdtParams p, const UdtLevel L)
 {
     cg::cluster_group cluster = cg::this_cluster();
-    const int CS = gm.cs, nv = gm.nv, n = p.n;
-    const int csh = 31 - __clz(CS);                     // CS is 1, 2, 4 or 8
+    const int CS = L.cs, nv = L.nv, n = L.n, jstop = L.jstop, joff = L.joff;
+    const int csh = 31 - __clz(CS);                      // CS is 1, 2, 4 or 8
     const int rank = (int)cluster.block_rank();
     const int mat = blockIdx.x / CS;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = gm.nwarps;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = L.nwarps;
     const int nloc = (n - rank + CS - 1) / CS;           // local columns: slot s <-> column s * CS + rank
 
     extern __shared__ __align__(16) double sm[];
@@ -212,11 +234,10 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
     int* candcol = perm + n;                             // [2][8]
     int* wbcol = candcol + 16;                           // [2][32]
 
-    const double* Ag = p.A + (long long)mat * p.strideA;
+    const double* Ag = L.A + (long long)mat * L.strideA;
+    const int* cmap = L.cmap ? L.cmap + (long long)mat * L.strideCmap : nullptr;
     double* Vg = p.Vwork + (long long)mat * p.strideV;
-    const int ld = p.ld, ldv = p.ldv;
-    long long* dbg = (blockIdx.x == 0) ? gm.dbg : nullptr;   // per-phase cycle counters of CTA 0 (debug)
-    long long tprev = dbg ? clock64() : 0;
+    const int ld = L.ld, ldv = p.ldv;
 
     // ---- load the panel into registers ------------------------------------------------------
     double a[8][RPL];
@@ -227,7 +248,7 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
         const int s = warp * 8 + c;
         const bool have = s < nloc;
         const int col = s * CS + rank;
-        const double sc = (have && p.colscale.mode) ? scale_at(p.colscale, mat, col) : 1.0;
+        const double sc = (have && joff == 0 && p.colscale.mode) ? scale_at(p.colscale, mat, col) : 1.0;
         double acc = 0.0;
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
@@ -288,31 +309,35 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
         }
     };
 
-    cluster_barrier();                                   // peers resident before any DSMEM store
+    if (CS > 1) cluster_barrier();                       // peers resident before any DSMEM store
+    else __syncthreads();
 
-    DQMC_TICK(0);
     double vprev[RPL];                                   // Householder vector of the previous step (stored late)
     bool store_prev = false;
 #pragma unroll
     for (int r = 0; r < RPL; ++r) vprev[r] = 0.0;
-    for (int j = 0; j < n; ++j) {
+    // Householder vector (0 .. 0 1 v) of step jj -> column joff + jj of V, rows joff .. ; rows < joff are zero
+    auto store_v = [&](int jj, const double (&vv)[RPL]) {
+        double* col = Vg + (long long)(joff + jj) * ldv;
+        for (int i = lane; i < joff; i += 32) col[i] = 0.0;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const int row = lane + 32 * r;
+            if (joff + row < ldv) col[joff + row] = vv[r];
+        }
+    };
+
+    for (int j = 0; j < jstop; ++j) {
         const int q = j & 1;
         // ---- pick and publish this CTA's best remaining column, then ONE cluster barrier ------
         warp_candidate(q);
-        DQMC_TICK(7);
         __syncthreads();
-        DQMC_TICK(8);
         publish(j);
-        DQMC_TICK(9);
-        cluster_arrive();
-        // the previous Householder vector (0 .. 0 1 v) goes to global memory (for Q) between arrive and
-        // wait, so that the release fence of the barrier never has to wait for these stores
-        if (store_prev) {
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) Vg[lane + 32 * r + (long long)(j - 1) * ldv] = vprev[r];
-        }
-        cluster_wait();
-        DQMC_TICK(10);
+        if (CS > 1) cluster_arrive(); else __syncthreads();
+        // the previous Householder vector goes to global memory (for Q) between arrive and wait, so
+        // that the release fence of the barrier never has to wait for these stores
+        if (store_prev) store_v(j - 1, vprev);
+        if (CS > 1) cluster_wait();
         // ---- global winner, identical in every CTA ------------------------------------------
         double bv = candval[q * 8]; int bc = candcol[q * 8], br = 0;
         for (int r = 1; r < CS; ++r) {
@@ -336,7 +361,6 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
             xi1 += nu;                                   // |xi1| >= sqrt(bv): never cancels
             rjj = -nu; tau = xi1 * copysign(rs, nu); inv = fast_rcp(xi1);
         }
-        DQMC_TICK(1);                                    // winner + reflector scalars
         const int r0 = j >> 5;                           // first register row that can be >= j
         double v[RPL];
 #pragma unroll
@@ -346,7 +370,7 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
             v[r] = (row < n) ? x : 0.0;
         }
         const unsigned long long m0 = (lane + 32 * r0 > j) ? ~0ull : 0ull;   // rows of register row r0 that are > j
-        const bool store_v = (rank == br && warp == 0);  // done after the barrier arrive, see below
+        const bool i_store_v = (rank == br && warp == 0);
         if (tid == 0) {
             const double ad = fabs(rjj);
             dvec[j] = (ad == 0.0) ? 1.0 : ad;
@@ -369,113 +393,157 @@ udt_reg_kernel(const UdtParams p, const UdtRegGeom gm)
             }
         }
 
-        DQMC_TICK(2);                                    // v, bookkeeping, retire
         // ---- apply H_j to the active columns of this warp, fused norm recompute -------------
         if (act != 0u) {                                 // warp-uniform
             col_dots<RPL>(a, v, act, part, r0);
-            DQMC_TICK(3);
             warp_allreduce8(part, lane);
-            DQMC_TICK(4);
-            col_update<RPL, true>(a, v, act, part, tau, m0, r0);
-            DQMC_TICK(5);
+            col_update<RPL, true>(a, v, part, tau, m0, r0);
             mynorm = warp_reduce8(part, lane);
-            DQMC_TICK(6);
         }
-        store_prev = store_v;
+        store_prev = i_store_v;
 #pragma unroll
         for (int r = 0; r < RPL; ++r) vprev[r] = v[r];
     }
-    if (store_prev) {
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) Vg[lane + 32 * r + (long long)(n - 1) * ldv] = vprev[r];
-    }
-    __threadfence();
-    cluster_barrier();       // V (global) of every step owner is visible cluster-wide; dvec/perm final
+    if (store_prev) store_v(jstop - 1, vprev);
+    __syncthreads();                                     // dvec / taus / perm / colstep of the last step visible
 
-    // ---- D, pivot, T ----------------------------------------------------------------------------
+    // ---- D, tau, pivot of this level ---------------------------------------------------------------
     if (rank == 0) {
-        double* Dg = p.D + (long long)mat * p.strideD;
-        int* pg = p.pivot ? p.pivot + (long long)mat * p.stridePivot : nullptr;
-        for (int i = tid; i < n; i += nwarps * 32) { Dg[i] = dvec[i]; if (pg) pg[i] = perm[i]; }
+        double* Dg = p.D + (long long)mat * p.strideD + joff;
+        double* tg = p.tau + (long long)mat * p.strideTau + joff;
+        int* pg = p.pivot ? p.pivot + (long long)mat * p.stridePivot + joff : nullptr;
+        for (int i = tid; i < jstop; i += nwarps * 32) {
+            Dg[i] = dvec[i]; tg[i] = taus[i];
+            if (pg) { const int pc = perm[i]; pg[i] = cmap ? cmap[pc] : pc; }
+        }
     }
+    // ---- rows joff .. of T (physical column order): finished columns completely, active ones up to jstop
     {
-        double* Tg = p.T + (long long)mat * p.strideT;
+        double* Tg = L.Tphys + (long long)mat * L.strideTp;
+        const int n_tot = p.n;
         double dinv[RPL];
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) { const int row = lane + 32 * r; dinv[r] = (row < n) ? 1.0 / dvec[row] : 0.0; }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int s = warp * 8 + c;
-            if (s < nloc) {
-                const int js = colstep[s];
-                const int oc = p.pivot_applied ? (s * CS + rank) : js;
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    const int row = lane + 32 * r;
-                    if (row < n) Tg[row + (long long)oc * ld] = (row <= js) ? a[c][r] * dinv[r] : 0.0;
-                }
-            }
-        }
-    }
-
-    DQMC_TICK(11);
-    // ---- explicit Q, backwards (UDT.jl:272-288); warps are independent from here on --------------
-    int cmax = -1;                                       // largest column owned by this warp
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int s = warp * 8 + c;
-        const int col = s * CS + rank;
-        if (s < nloc) cmax = col;
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) a[c][r] = (s < nloc && lane + 32 * r == col) ? 1.0 : 0.0;
-    }
-    if (cmax >= 0 && !gm.skip_q) {
-        // reflector k only touches columns >= k, so this warp starts at k = cmax
-        double vn[RPL];
-        auto load_v = [&](int k, double (&dst)[RPL]) {   // V columns are stored complete (0 .. 0 1 v), ldv = 32 * RPL
-            const double* src = Vg + (long long)(k < 0 ? 0 : k) * ldv + lane;
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) dst[r] = src[32 * r];
-        };
-        load_v(cmax, vn);
-        for (int k = cmax; k >= 0; --k) {
-            double v[RPL];
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) v[r] = vn[r];
-            load_v(k - 1, vn);                           // prefetch the next vector from L2
-            const double tau = taus[k];
-            const int r0 = k >> 5;
-            unsigned m = 0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int s = warp * 8 + c;
-                if (s < nloc && s * CS + rank >= k) m |= 1u << c;
-            }
-            col_dots<RPL>(a, v, m, part, r0);
-            warp_allreduce8(part, lane);
-            col_update<RPL, false>(a, v, m, part, tau, 0ull, r0);
-        }
-    }
-    DQMC_TICK(12);
-    {
-        double* Ug = p.U + (long long)mat * p.strideU;
+        for (int r = 0; r < RPL; ++r) { const int row = lane + 32 * r; dinv[r] = (row < jstop) ? 1.0 / dvec[row] : 0.0; }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const int s = warp * 8 + c;
             if (s < nloc) {
                 const int col = s * CS + rank;
+                const int pc = cmap ? cmap[col] : col;
+                const int js = colstep[s];
+                double* tc = Tg + joff + (long long)pc * p.ld;
+                if (js >= 0) {                           // pivoted at this level: rows <= js are R, the rest 0
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r) {
+                        const int row = lane + 32 * r;
+                        if (joff + row < n_tot) tc[row] = (row <= js) ? a[c][r] * dinv[r] : 0.0;
+                    }
+                } else {                                 // still active: rows < jstop are final (R12)
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r) {
+                        const int row = lane + 32 * r;
+                        if (row < jstop) tc[row] = a[c][r] * dinv[r];
+                    }
+                }
+            }
+        }
+    }
+    // ---- export the compacted trailing block for the next level --------------------------------------
+    if (jstop < n) {
+        double* Sg = L.S + (long long)mat * L.strideS;
+        int* cmo = L.cmap_out + (long long)mat * L.strideCmapOut;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int s = warp * 8 + c;
+            if (s < nloc && colstep[s] < 0) {
+                const int col = s * CS + rank;
+                // compact index = number of still-active columns with a smaller index
+                //               = col - #(pivoted columns < col); the pivoted set is perm[0 .. jstop)
+                int cnt = 0;
+                for (int i = lane; i < jstop; i += 32) cnt += (perm[i] < col) ? 1 : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                const int k = col - cnt;
+                if (lane == 0) cmo[k] = cmap ? cmap[col] : col;
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) {
                     const int row = lane + 32 * r;
-                    if (row < n) Ug[row + (long long)col * ld] = a[c][r];
+                    if (row >= jstop && row < n) Sg[(row - jstop) + (long long)k * L.ldS] = a[c][r];
                 }
             }
         }
     }
 }
 
+// ================================================================================================
+// explicit Q = H_0 ... H_{n-1} I, backwards (UDT.jl:272-288).  One CTA = 64 columns, warps independent.
+// ================================================================================================
 template <int RPL>
-static cudaError_t launch_reg(const UdtParams& p, const UdtRegGeom& g, cudaStream_t st)
+__global__ void __launch_bounds__(256)
+udt_formq_kernel(const UdtParams p, int cols_per_cta)
+{
+    const int n = p.n, ld = p.ld, ldv = p.ldv;
+    const int ctas_per_mat = (n + cols_per_cta - 1) / cols_per_cta;
+    const int mat = blockIdx.x / ctas_per_mat, part_i = blockIdx.x - mat * ctas_per_mat;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col0 = part_i * cols_per_cta + warp * 8;   // this warp owns columns col0 .. col0 + 7
+    if (col0 >= n) return;
+    const double* Vg = p.Vwork + (long long)mat * p.strideV;
+    const double* tg = p.tau + (long long)mat * p.strideTau;
+    double* Ug = p.U + (long long)mat * p.strideU;
+
+    double a[8][RPL], part[8];
+    int cmax = -1;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int col = col0 + c;
+        if (col < n) cmax = col;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) a[c][r] = (col < n && lane + 32 * r == col) ? 1.0 : 0.0;
+    }
+    // reflector k only touches columns >= k, so this warp starts at k = cmax
+    double vn[RPL], taun;
+    auto load_v = [&](int k, double (&dst)[RPL], double& t) {   // V columns are stored complete (0 .. 0 1 v)
+        const int kk = k < 0 ? 0 : k;
+        const double* src = Vg + (long long)kk * ldv + lane;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) dst[r] = src[32 * r];
+        t = tg[kk];
+    };
+    load_v(cmax, vn, taun);
+    for (int k = cmax; k >= 0; --k) {
+        double v[RPL];
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) v[r] = vn[r];
+        const double tau = taun;
+        load_v(k - 1, vn, taun);                         // prefetch the next vector from L2
+        const int r0 = k >> 5;
+        unsigned m = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (col0 + c < n && col0 + c >= k) m |= 1u << c;
+        col_dots<RPL>(a, v, m, part, r0);
+        warp_allreduce8(part, lane);
+        col_update<RPL, false>(a, v, part, tau, 0ull, r0);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int col = col0 + c;
+        if (col < n) {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const int row = lane + 32 * r;
+                if (row < n) Ug[row + (long long)col * ld] = a[c][r];
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+template <int RPL>
+static cudaError_t launch_steps(const UdtParams& p, const UdtLevel& g, cudaStream_t st)
 {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.batch * g.cs));
@@ -487,45 +555,80 @@ static cudaError_t launch_reg(const UdtParams& p, const UdtRegGeom& g, cudaStrea
     at[0].val.clusterDim.x = (unsigned)g.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     ++g_kernel_launches;
-    return cudaLaunchKernelEx(&cfg, udt_reg_kernel<RPL>, p, g);
+    return cudaLaunchKernelEx(&cfg, udt_steps_kernel<RPL>, p, g);
 }
 
-bool udt_reg_supported(int n) { UdtRegGeom g; return udt_reg_geometry(n, g); }
+template <int RPL>
+static cudaError_t launch_formq(const UdtParams& p, cudaStream_t st)
+{
+    const int cols_per_cta = 64;
+    const int ctas = p.batch * ((p.n + cols_per_cta - 1) / cols_per_cta);
+    ++g_kernel_launches;
+    udt_formq_kernel<RPL><<<(unsigned)ctas, 256, 0, st>>>(p, cols_per_cta);
+    return cudaGetLastError();
+}
+
+#define DQMC_RPL_SWITCH(rpl, CALL) \
+    switch (rpl) { \
+    case 1: { constexpr int R = 1; err = CALL; } break; case 2: { constexpr int R = 2; err = CALL; } break; \
+    case 3: { constexpr int R = 3; err = CALL; } break; case 4: { constexpr int R = 4; err = CALL; } break; \
+    case 5: { constexpr int R = 5; err = CALL; } break; case 6: { constexpr int R = 6; err = CALL; } break; \
+    case 7: { constexpr int R = 7; err = CALL; } break; case 8: { constexpr int R = 8; err = CALL; } break; \
+    default: { constexpr int R = 9; err = CALL; } break; }
+
+bool udt_reg_supported(int n) { UdtLevel g{}; return udt_level_geometry(n, g); }
+
+// scratch needed per matrix besides Vwork: Tphys (ld * n doubles), the trailing-block buffers
+// ((n/2)^2 + (n/4)^2 + ... < n^2 / 2 doubles, rounded-up leading dimensions) and two column maps (2 n ints)
+size_t udt_reg_scratch_doubles(int n, int ld) { return (size_t)ld * n + (size_t)(n + 2) * (n + 2) / 2 + 64; }
+size_t udt_reg_scratch_ints(int n) { return (size_t)2 * n + 16; }
 
 cudaError_t launch_udt_reg(const UdtParams& p, cudaStream_t st)
 {
     if (p.batch <= 0) return cudaSuccess;
-    UdtRegGeom g;
-    if (!udt_reg_geometry(p.n, g)) return cudaErrorInvalidConfiguration;
-    static const bool want_dbg = getenv("DQMC_UDT_DBG") != nullptr;
-    static long long* dbg_buf = nullptr;
-    if (want_dbg) {
-        if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
-        cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), st);
-        g.dbg = dbg_buf;
+    if (!p.scratch || !p.iscratch) return cudaErrorInvalidValue;
+    static const bool one_level = getenv("DQMC_UDT_ONE_LEVEL") != nullptr;   // A/B knob
+    const int n = p.n;
+    // scratch layout: [Tphys: batch x ld*n] [S level 0: batch x ...] [S level 1: batch x ...] ...
+    double* Tphys_base = p.scratch;
+    const long long strideTp = (long long)p.ld * n;
+    double* S_base = p.scratch + (size_t)p.batch * strideTp;
+    const bool direct_T = p.pivot_applied != 0;          // physical order IS the requested output
+
+    int nk = n, joff = 0, level = 0;
+    const double* Ain = p.A; long long strideIn = p.strideA; int ldin = p.ld;
+    const int* cmap_in = nullptr; long long strideCm = 0;
+    size_t s_off = 0;
+    cudaError_t err = cudaSuccess;
+    while (nk > 0) {
+        UdtLevel g{};
+        if (!udt_level_geometry(nk, g)) return cudaErrorInvalidConfiguration;
+        int jstop = nk;
+        if (!one_level && nk > 64) jstop = nk / 2;
+        g.n = nk; g.jstop = jstop; g.joff = joff; g.ld = ldin;
+        g.A = Ain; g.strideA = strideIn; g.cmap = cmap_in; g.strideCmap = strideCm;
+        g.Tphys = direct_T ? p.T : Tphys_base; g.strideTp = direct_T ? p.strideT : strideTp;
+        const int n2 = nk - jstop;
+        if (n2 > 0) {
+            g.ldS = (n2 + 1) & ~1; g.strideS = (long long)g.ldS * n2;
+            g.S = S_base + s_off; s_off += (size_t)p.batch * g.strideS;
+            g.cmap_out = p.iscratch + (size_t)(level & 1) * p.batch * n; g.strideCmapOut = n;
+        }
+        DQMC_RPL_SWITCH(g.rpl, (launch_steps<R>(p, g, st)))
+        if (err != cudaSuccess) return err;
+        if (n2 > 0) {
+            Ain = g.S; strideIn = g.strideS; ldin = g.ldS;
+            cmap_in = g.cmap_out; strideCm = n;
+        }
+        joff += jstop; nk = n2; ++level;
     }
-    cudaError_t err;
-    switch (g.rpl) {
-    case 1: err = launch_reg<1>(p, g, st); break;
-    case 2: err = launch_reg<2>(p, g, st); break;
-    case 3: err = launch_reg<3>(p, g, st); break;
-    case 4: err = launch_reg<4>(p, g, st); break;
-    case 5: err = launch_reg<5>(p, g, st); break;
-    case 6: err = launch_reg<6>(p, g, st); break;
-    case 7: err = launch_reg<7>(p, g, st); break;
-    case 8: err = launch_reg<8>(p, g, st); break;
-    default: err = launch_reg<9>(p, g, st); break;
-    }
-    if (want_dbg && err == cudaSuccess) {
-        long long h[16];
-        cudaStreamSynchronize(st);
-        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-        static const char* nm[13] = {"load+first publish", "winner+reflector", "v+retire", "dots", "allreduce8", "update+norms",
-                                     "reduce8", "warp candidate", "syncthreads", "publish", "vstore+cluster wait", "outputs D/T", "form Q"};
-        fprintf(stderr, "[udt dbg n=%d cs=%d] cycles of CTA 0 thread 0:", p.n, g.cs);
-        for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", nm[i], h[i]);
-        fprintf(stderr, "\n");
-    }
+    // Q
+    const int rpl = (n + 31) / 32;
+    DQMC_RPL_SWITCH(rpl, (launch_formq<R>(p, st)))
+    if (err != cudaSuccess) return err;
+    // the Val(false) form wants the columns of D^-1 R in pivot (logical) order
+    if (!direct_T)
+        err = launch_permute_cols(Tphys_base, p.T, p.pivot, n, p.ld, strideTp, p.stridePivot, p.batch, st);
     return err;
 }
 
