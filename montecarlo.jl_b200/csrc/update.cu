@@ -42,6 +42,17 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
+__device__ __forceinline__ double upd_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 static inline int update_ldu(int n) { return n + (((4 - n) % 16) + 16) % 16; }   // == 4 mod 16
 
 int update_pick_kb(int n, int nb)
@@ -58,11 +69,12 @@ int update_pick_kb(int n, int nb)
 struct UpdShared {
     int dec[2];
     double coef[2][2];
+    double gdiag[2][32];     // current G_ii of the sites of the block, per flavor (kb <= 32)
 };
 
-#define UPD_TICK(slot) do { if (dbg) { const long long t__ = clock64(); if (tid == 0) dbg[slot] += t__ - tprev; tprev = t__; } } while (0)
+#define UPD_TICK(slot) do { if (dbg) { const long long t__ = clock64(); dacc[slot] += t__ - tprev; tprev = t__; } } while (0)
 
-__global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const int ldu, const double em2a, const double ep2a,
+__global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const int ldu, const double em2a, const double ep2a,
                                                       long long* dbg_all)
 {
     extern __shared__ __align__(16) double sm[];
@@ -71,6 +83,7 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
     const int chain = blockIdx.x;
     long long* dbg = (blockIdx.x == 0) ? dbg_all : nullptr;
     long long tprev = dbg ? clock64() : 0;
+    long long dacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // per-phase cycles (debug only, thread-local)
 
     double* Uc = sm;                                   // [nb][kb][ldu]   columns of G0 -> u_a
     double* Wr = Uc + (size_t)nb * kb * ldu;           // [nb][kb][ldu]   rows of G0    -> w_a
@@ -94,22 +107,26 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
 
     for (int i0 = 0; i0 < n; i0 += kb) {
         const int kbc = (n - i0 < kb) ? (n - i0) : kb;
+        UPD_TICK(8);                   // flush of the previous block
         __syncthreads();               // previous flush (global G) and sconf visible
+        UPD_TICK(9);
         // ---- stage the kbc columns and rows of G ---------------------------------
-        for (int e = tid; e < nb * kbc * n; e += NT) {
-            const int b = e / (kbc * n), f = e - b * (kbc * n);
+        for (int b = 0; b < nb; ++b) {
             const double* Gb = G + (long long)b * p.strideG;
-            const int j = f / n, r = f - j * n;
-            cp_async8(Uc + ((size_t)b * kb + j) * ldu + r, Gb + r + (long long)(i0 + j) * ld);
-        }
-        for (int e = tid; e < nb * kbc * n; e += NT) {
-            const int b = e / (kbc * n), f = e - b * (kbc * n);
-            const double* Gb = G + (long long)b * p.strideG;
-            const int c = f / kbc, j = f - c * kbc;
-            cp_async8(Wr + ((size_t)b * kb + j) * ldu + c, Gb + (i0 + j) + (long long)c * ld);
+            double* ub = Uc + (size_t)b * kb * ldu;
+            double* wb = Wr + (size_t)b * kb * ldu;
+            for (int j = 0; j < kbc; ++j)                       // columns: contiguous in r
+                for (int r = tid; r < n; r += NT) cp_async8(ub + (size_t)j * ldu + r, Gb + r + (long long)(i0 + j) * ld);
+            if (lane < kbc)                                     // rows: a warp copies the kbc contiguous entries of one column
+                for (int c = warp; c < n; c += nwarps) cp_async8(wb + (size_t)lane * ldu + c, Gb + (i0 + lane) + (long long)c * ld);
         }
         UPD_TICK(0);
         cp_async_wait_all();
+        __syncthreads();
+        if (tid < nb * kbc) {                                   // G_ii of the block's sites
+            const int b = tid / kbc, x = tid - b * kbc;
+            sh->gdiag[b][x] = Uc[((size_t)b * kb + x) * ldu + i0 + x];
+        }
         __syncthreads();
         UPD_TICK(1);
 
@@ -124,12 +141,8 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
                 const double e_mdE = (x > 0.0) ? ep2a : em2a;
                 double Rv[2], Dl[2];
                 for (int b = 0; b < nb; ++b) {
-                    const double* ub = Uc + (size_t)b * kb * ldu;
-                    const double* wb = Wr + (size_t)b * kb * ldu;
-                    // slots a < k hold -u_a (negated so that the flush needs no FP64 negation)
-                    double part = (lane < k) ? ub[(size_t)lane * ldu + i] * wb[(size_t)lane * ldu + i] : 0.0;
-                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                    const double gii = ub[(size_t)j * ldu + i] + part;
+                    // current G_ii = G0_ii - sum_a u_a[i] w_a[i], kept as a running value per site of the block
+                    const double gii = sh->gdiag[b][j];
                     Dl[b] = ((p.kind == 1 && b == 1) ? e_mdE : e_dE) - 1.0;
                     Rv[b] = 1.0 + Dl[b] * (1.0 - gii);
                 }
@@ -150,8 +163,12 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
                     if (p.probs) p.probs[(long long)chain * p.tstride + i] = prob;
                     if (p.decisions) p.decisions[(long long)chain * p.tstride + i] = (unsigned char)acc;
                     sh->dec[j & 1] = acc;
-                    for (int b = 0; b < nb; ++b) sh->coef[j & 1][b] = Dl[b] / Rv[b];
-                    if (acc) { sconf[i] = (int8_t)(-sconf[i]); conf[i] = sconf[i]; }
+                    if (acc) {
+                        // Delta / R (vldiv22!, fields.jl:176-216) via a Newton reciprocal: the library division is
+                        // a ~15-deep dependent FP64 chain on the serial path of every accepted flip
+                        for (int b = 0; b < nb; ++b) sh->coef[j & 1][b] = Dl[b] * upd_rcp(Rv[b]);
+                        sconf[i] = (int8_t)(-sconf[i]); conf[i] = sconf[i];
+                    }
                 }
             }
             if (warp == 0) UPD_TICK(2);
@@ -160,20 +177,32 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
             const int acc = sh->dec[j & 1];
             if (acc) {
                 // ---- new delayed factors (fields.jl:271-286) ------------------------------
-                for (int e = tid; e < nb * n; e += NT) {
-                    const int b = (e >= n) ? 1 : 0, r = e - b * n;
-                    double* ub = Uc + (size_t)b * kb * ldu;
-                    double* wb = Wr + (size_t)b * kb * ldu;
-                    const double coef = sh->coef[j & 1][b];
-                    double col = ub[(size_t)j * ldu + r];
-                    double row = wb[(size_t)j * ldu + r];
+                double* ub0 = Uc; double* wb0 = Wr;
+                double* ub1 = Uc + (size_t)(nb - 1) * kb * ldu; double* wb1 = Wr + (size_t)(nb - 1) * kb * ldu;
+                const double coef0 = sh->coef[j & 1][0], coef1 = sh->coef[j & 1][nb - 1];
+                for (int r = tid; r < n; r += NT) {
+                    // both flavor blocks in one loop body: twice the independent FMA chains per iteration
+                    double col0 = ub0[(size_t)j * ldu + r], row0 = wb0[(size_t)j * ldu + r];
+                    double col1 = ub1[(size_t)j * ldu + r], row1 = wb1[(size_t)j * ldu + r];
+#pragma unroll 2
                     for (int a = 0; a < k; ++a) {
-                        col += ub[(size_t)a * ldu + r] * wb[(size_t)a * ldu + i];
-                        row += ub[(size_t)a * ldu + i] * wb[(size_t)a * ldu + r];
+                        col0 = fma(ub0[(size_t)a * ldu + r], wb0[(size_t)a * ldu + i], col0);
+                        row0 = fma(ub0[(size_t)a * ldu + i], wb0[(size_t)a * ldu + r], row0);
+                        if (nb == 2) {
+                            col1 = fma(ub1[(size_t)a * ldu + r], wb1[(size_t)a * ldu + i], col1);
+                            row1 = fma(ub1[(size_t)a * ldu + i], wb1[(size_t)a * ldu + r], row1);
+                        }
                     }
                     // element (slot k, r) is only ever touched by this thread until the barrier
-                    ub[(size_t)k * ldu + r] = col - ((r == i) ? 1.0 : 0.0);     // -u = G[:, i] - e_i
-                    wb[(size_t)k * ldu + r] = coef * row;
+                    const double un0 = col0 - ((r == i) ? 1.0 : 0.0), wn0 = coef0 * row0;      // -u = G[:, i] - e_i
+                    ub0[(size_t)k * ldu + r] = un0; wb0[(size_t)k * ldu + r] = wn0;
+                    const bool inblk = (r >= i0) && (r < i0 + kbc);
+                    if (inblk) sh->gdiag[0][r - i0] += un0 * wn0;
+                    if (nb == 2) {
+                        const double un1 = col1 - ((r == i) ? 1.0 : 0.0), wn1 = coef1 * row1;
+                        ub1[(size_t)k * ldu + r] = un1; wb1[(size_t)k * ldu + r] = wn1;
+                        if (inblk) sh->gdiag[1][r - i0] += un1 * wn1;
+                    }
                 }
                 // the loop above reads slot-a entries at index i written by other threads in
                 // earlier steps (already separated by barriers) and slot j/k entries of its own r.
@@ -192,14 +221,18 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
             const int tiles = (n + 31) / 32;
             const int k4 = (k + 3) / 4;
             {
-                for (int bt = warp; bt < nb * tiles * tiles; bt += nwarps) {
-                    const int b = bt / (tiles * tiles), tile = bt - b * (tiles * tiles);
-                    double* Gb = G + (long long)b * p.strideG;
-                    const double* ub = Uc + (size_t)b * kb * ldu;
-                    const double* wb = Wr + (size_t)b * kb * ldu;
-                    const int tm = (tile % tiles) * 32, tn = (tile / tiles) * 32;
-                    // acc <- G tile (all loads in flight together), then acc += (-u) w^T, then store
-                    double acc2[4][4][2];
+                // each warp walks its tiles with a one-tile look-ahead: the loads of G for tile t+1 are in
+                // flight while tile t is updated and stored (the flush is bound by memory-level parallelism)
+                const int ntl = nb * tiles * tiles;
+                auto tile_ptr = [&](int bt, int& tm, int& tn, int& b) -> double* {
+                    b = bt / (tiles * tiles);
+                    const int tile = bt - b * (tiles * tiles);
+                    tm = (tile % tiles) * 32; tn = (tile / tiles) * 32;
+                    return G + (long long)b * p.strideG;
+                };
+                auto load_tile = [&](int bt, double (&dst)[4][4][2]) {
+                    int tm, tn, b;
+                    const double* Gb = tile_ptr(bt, tm, tn, b);
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi) {
                         const int r = tm + mi * 8 + g;
@@ -208,9 +241,19 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int c = tn + nj * 8 + 2 * t + e;
-                                acc2[mi][nj][e] = (r < n && c < n) ? Gb[r + (long long)c * ld] : 0.0;
+                                dst[mi][nj][e] = (r < n && c < n) ? Gb[r + (long long)c * ld] : 0.0;
                             }
                     }
+                };
+                double cur[4][4][2], nxt[4][4][2];
+                if (warp < ntl) load_tile(warp, cur);
+                for (int bt = warp; bt < ntl; bt += nwarps) {
+                    const bool more = bt + nwarps < ntl;
+                    if (more) load_tile(bt + nwarps, nxt);
+                    int tm, tn, b;
+                    double* Gb = tile_ptr(bt, tm, tn, b);
+                    const double* ub = Uc + (size_t)b * kb * ldu;
+                    const double* wb = Wr + (size_t)b * kb * ldu;
                     for (int kk = 0; kk < k4; ++kk) {
                         const int a = kk * 4 + t;
                         const bool live = a < k;
@@ -229,18 +272,18 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
                         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                             for (int nj = 0; nj < 4; ++nj)
-                                dmma884u(acc2[mi][nj][0], acc2[mi][nj][1], af[mi], bf[nj]);
+                                dmma884u(cur[mi][nj][0], cur[mi][nj][1], af[mi], bf[nj]);
                     }
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi) {
                         const int r = tm + mi * 8 + g;
-                        if (r >= n) continue;
 #pragma unroll
                         for (int nj = 0; nj < 4; ++nj)
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int c = tn + nj * 8 + 2 * t + e;
-                                if (c < n) Gb[r + (long long)c * ld] = acc2[mi][nj][e];
+                                if (r < n && c < n) Gb[r + (long long)c * ld] = cur[mi][nj][e];
+                                cur[mi][nj][e] = nxt[mi][nj][e];
                             }
                     }
                 }
@@ -249,6 +292,7 @@ __global__ void __launch_bounds__(384) update_kernel(const UpdateParams p, const
     }
 
     UPD_TICK(7);
+    if (dbg && tid == 0) { for (int i = 0; i < 10; ++i) dbg[i] = dacc[i]; }
     if (tid == 0) {
         if (p.accepted) p.accepted[chain] += accepted;
         if (p.stats && neg_cnt > 0.0) {
@@ -264,7 +308,7 @@ cudaError_t launch_update(const UpdateParams& p, cudaStream_t st)
     const int ldu = update_ldu(p.n);
     int nt = ((p.n + 31) / 32) * 32;             // one thread per row (flavor blocks in turn)
     if (nt < 64) nt = 64;
-    if (nt > 384) nt = 384;
+    if (nt > 256) nt = 256;
     const size_t smem = (size_t)p.nb * 2 * p.kb * ldu * sizeof(double) + sizeof(UpdShared) + (size_t)p.n * 9 + 16;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     static size_t configured = 0;
@@ -287,10 +331,10 @@ cudaError_t launch_update(const UpdateParams& p, cudaStream_t st)
         long long h[16];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-        static const char* nm[8] = {"sync+issue staging", "staging wait", "decision(warp0)", "wait decision", "accept update", "sync after accept",
-                                    "flush(prev)+loop", "tail"};
+        static const char* nm[10] = {"issue staging", "staging wait", "decision(warp0)", "wait decision", "accept update", "sync after accept",
+                                     "pre-flush", "tail", "flush", "sync after flush"};
         fprintf(stderr, "[upd dbg n=%d kb=%d] cycles of CTA 0 thread 0:", p.n, p.kb);
-        for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%lld", nm[i], h[i]);
+        for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%lld", nm[i], h[i]);
         fprintf(stderr, "\n");
     }
     return err;
