@@ -287,7 +287,10 @@ typedef struct ref_chain {
     const double *uniforms;              /* optional table [2M][N] for the current sweep */
     int64_t step_in_sweep;
     ref_stats stats;
+    void *ut;                            /* UnequalTimeStack (dqmc_ref_ut.inc.c), lazily allocated */
 } ref_chain;
+
+static void ut_free(ref_chain *c);
 
 static double *dalloc(size_t k) { return (double *)calloc(k ? k : 1, sizeof(double)); }
 
@@ -338,6 +341,7 @@ ref_chain *ref_chain_create(int N, int M, int nb, int kind, int C, const int *rf
 void ref_chain_destroy(ref_chain *c)
 {
     if (!c) return;
+    ut_free(c);
     free(c->rfirst); free(c->rlast); free(c->conf); free(c->u_stack); free(c->t_stack);
     free(c->d_stack); free(c->greens); free(c->greens_temp); free(c->Ul); free(c->Ur);
     free(c->Tl); free(c->Tr); free(c->tmp1); free(c->tmp2); free(c->curr_U); free(c->Dl);
@@ -894,3 +898,6 @@ double ref_run_chains(ref_chain **chains, int nchains, int nthreads, int warm, i
     pthread_mutex_destroy(&j.mu);
     return dt;
 }
+
+/* unequal-time Green's functions: UnequalTimeStack + CombinedGreensIterator */
+#include "dqmc_ref_ut.inc.c"

@@ -34,7 +34,8 @@ def build(force: bool = False) -> Path:
     so = _HERE / "libdqmc_ref.so"
     src = _HERE / "dqmc_ref.c"
     hdr = _HERE.parent / "include" / "dqmc_rng.h"
-    stale = (not so.exists()) or so.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime)
+    deps = [src, _HERE / "dqmc_ref_ut.inc.c", hdr]
+    stale = (not so.exists()) or so.stat().st_mtime < max(d.stat().st_mtime for d in deps)
     if force or stale:
         subprocess.check_call(["make", "-C", str(_HERE), "-B", "libdqmc_ref.so"],
                               stdout=subprocess.DEVNULL)
@@ -79,6 +80,18 @@ def lib():
         L.ref_max_threads.restype = C.c_int
         L.ref_run_chains.restype = C.c_double
         L.ref_run_chains.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, c_i64_p]
+        # unequal-time path (dqmc_ref_ut.inc.c)
+        L.ref_ut_build_stack.argtypes = [C.c_void_p]
+        L.ref_ut_lazy_build.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_ut_get_array.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p]
+        L.ref_ut_calculate_greens.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p]
+        L.ref_ut_greens.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p]
+        L.ref_find_range_with_value.restype = C.c_int
+        L.ref_find_range_with_value.argtypes = [C.c_void_p, C.c_int]
+        L.ref_cgi_first.restype = C.c_int
+        L.ref_cgi_first.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
+        L.ref_cgi_next.restype = C.c_int
+        L.ref_cgi_next.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]
         _LIB = L
     return _LIB
 
@@ -272,6 +285,47 @@ class RefChain:
             acc = lib().ref_local_sweep(self._h, u, f, _dp(probs), dec.ctypes.data_as(c_u8_p))
             return acc, probs, dec
         return lib().ref_local_sweep(self._h, u, f, None, None)
+
+    # ---- unequal-time stack (unequal_time_stack.jl) and CombinedGreensIterator (greens_iterators.jl)
+    def ut_build_stack(self):
+        lib().ref_ut_build_stack(self._h)
+
+    def ut_lazy_build(self, forward_upto=0, backward_downto=0):
+        lib().ref_ut_lazy_build(self._h, int(forward_upto), int(backward_downto))
+
+    def ut_array(self, which, slot):
+        """which: forward_u/d/t, backward_u/d/t, inv_u/d/t; slot 0-based."""
+        names = ["forward_u", "forward_d", "forward_t", "backward_u", "backward_d", "backward_t",
+                 "inv_u", "inv_d", "inv_t"]
+        w = names.index(which)
+        out = np.zeros((self.N, self.nb), order="F") if w % 3 == 1 else self._mat()
+        lib().ref_ut_get_array(self._h, w, int(slot), _dp(out))
+        return out
+
+    def find_range_with_value(self, val):
+        return lib().ref_find_range_with_value(self._h, int(val))
+
+    def ut_calculate_greens(self, k, l):
+        """calculate_greens(mc, k, l): effective G(k <- l), shape (N, N, nb)."""
+        g = self._mat()
+        lib().ref_ut_calculate_greens(self._h, int(k), int(l), _dp(g))
+        return g
+
+    def ut_greens(self, k, l):
+        """greens(mc, k, l): measured G(k <- l)."""
+        g = self._mat()
+        lib().ref_ut_greens(self._h, int(k), int(l), _dp(g))
+        return g
+
+    def combined_greens_iterator(self, recalculate=None, start=0, stop=None):
+        """Yields (l, G0l, Gl0, Gll) like CombinedGreensIterator (greens_iterators.jl:154-435)."""
+        recalculate = 2 * self.safe_mult if recalculate is None else int(recalculate)
+        stop = self.M if stop is None else int(stop)
+        bufs = [self._mat() for _ in range(3)]
+        nxt = lib().ref_cgi_first(self._h, recalculate, int(start), stop, self.safe_mult, *[_dp(b) for b in bufs])
+        while nxt >= 0:
+            yield (nxt - 1, *[b.copy() for b in bufs])
+            nxt = lib().ref_cgi_next(self._h, nxt, *[_dp(b) for b in bufs])
 
     def set_sweep_index(self, s):
         lib().ref_set_sweep_index(self._h, int(s))
