@@ -121,6 +121,24 @@ int32_t dqmc_get_stats(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, dqmc_stat
  * (stack.jl:13-22); matrices N x N x n_flavors, vectors N x n_flavors; slot is 1-based. */
 int32_t dqmc_get_stack_array(dqmc_ctx* ctx, int32_t chain, int32_t which, int32_t slot, double* out);
 
+/* ---- unequal-time Green's functions (UnequalTimeStack, src/flavors/DQMC/unequal_time_stack.jl) ------- */
+/* build_stack(mc, mc.ut_stack) (:128-185): forward, backward and inverse UDT stacks from the current conf. */
+int32_t dqmc_ut_build_stack(dqmc_ctx* ctx);
+/* lazy_build_forward!(mc, s, upto) / lazy_build_backward!(mc, s, downto) (:207-270); 0 skips that side. */
+int32_t dqmc_ut_lazy_build(dqmc_ctx* ctx, int32_t forward_upto, int32_t backward_downto);
+/* measured != 0: greens(mc, k, l) (:302-320), G(k <- l) with the exp(+-dtau T/2) transform;
+ * measured == 0: calculate_greens(mc, k, l) (:322-335), the effective G(k, l).  0 <= k, l <= M; all chains,
+ * N x N x n_flavors x n_chains.  Overwrites Ul..Tr like the reference and ends a running iteration. */
+int32_t dqmc_ut_greens(dqmc_ctx* ctx, int32_t k, int32_t l, int32_t measured, double* G);
+/* which: 0/1/2 forward_u/d/t_stack, 3/4/5 backward_u/d/t_stack, 6/7/8 inv_u/d/t_stack; slot 1-based. */
+int32_t dqmc_ut_get_stack_array(dqmc_ctx* ctx, int32_t chain, int32_t which, int32_t slot, double* out);
+/* CombinedGreensIterator(mc; recalculate, start, stop) (measurements/greens_iterators.jl:154-435): every
+ * dqmc_cgi_next produces the triple (G(0,l), G(l,0), G(l,l)) of the next l (measured Green's functions of all
+ * chains; any of the three pointers may be NULL to leave that matrix on the device) and stores l, or -1 once
+ * l > stop.  The stack must be at (slice 1, direction +1) or G(0,0) is recomputed from the ut stack. */
+int32_t dqmc_cgi_begin(dqmc_ctx* ctx, int32_t recalculate, int32_t start, int32_t stop, int32_t safe_mult);
+int32_t dqmc_cgi_next(dqmc_ctx* ctx, int32_t* l, double* G0l, double* Gl0, double* Gll);
+
 /* ---- observables ---------------------------------------------------------------------------- */
 /* Accumulate the measured Green's function of every chain into device accumulators
  * {count, sum, sum of squares} (stands in for push!(LogBinner, G), measurements/generic.jl:586). */

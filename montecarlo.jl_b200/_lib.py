@@ -76,6 +76,12 @@ def load():
         "dqmc_calculate_greens_at": (i32, [vp, i32, i32, dp]),
         "dqmc_get_stats": (i32, [vp, i32, i32, C.POINTER(Stats)]),
         "dqmc_get_stack_array": (i32, [vp, i32, i32, i32, dp]),
+        "dqmc_ut_build_stack": (i32, [vp]),
+        "dqmc_ut_lazy_build": (i32, [vp, i32, i32]),
+        "dqmc_ut_greens": (i32, [vp, i32, i32, i32, dp]),
+        "dqmc_ut_get_stack_array": (i32, [vp, i32, i32, i32, dp]),
+        "dqmc_cgi_begin": (i32, [vp, i32, i32, i32, i32]),
+        "dqmc_cgi_next": (i32, [vp, i32p, dp, dp, dp]),
         "dqmc_accumulate_greens": (i32, [vp]),
         "dqmc_observable_buffer": (i32, [vp, C.POINTER(vp), i64p]),
         "dqmc_reduce_observables": (i32, [vp, vp]),

@@ -209,6 +209,44 @@ class Context:
         self._ck(self._L.dqmc_get_stack_array(self._h, int(chain), w, int(slot), _dp(out)))
         return out
 
+    # ------------------------------------------------------------------ unequal-time Green's functions
+    _UT_WHICH = {"forward_u": 0, "forward_d": 1, "forward_t": 2, "backward_u": 3, "backward_d": 4,
+                 "backward_t": 5, "inv_u": 6, "inv_d": 7, "inv_t": 8}
+
+    def ut_build_stack(self):
+        """build_stack(mc, mc.ut_stack) (unequal_time_stack.jl:128-185)."""
+        self._ck(self._L.dqmc_ut_build_stack(self._h))
+
+    def ut_lazy_build(self, forward_upto=0, backward_downto=0):
+        self._ck(self._L.dqmc_ut_lazy_build(self._h, int(forward_upto), int(backward_downto)))
+
+    def ut_stack_array(self, which, slot=1, chain=0):
+        w = self._UT_WHICH[which]
+        out = np.zeros((self.N, self.nb), order="F") if w % 3 == 1 else np.zeros((self.N, self.N, self.nb), order="F")
+        self._ck(self._L.dqmc_ut_get_stack_array(self._h, int(chain), w, int(slot), _dp(out)))
+        return out
+
+    def ut_greens(self, k, l, measured=True):
+        """greens(mc, k, l) (measured=True) / calculate_greens(mc, k, l) for all chains -> (N, N, nb, B)."""
+        out = np.zeros(self._gshape(self.B), order="F")
+        self._ck(self._L.dqmc_ut_greens(self._h, int(k), int(l), int(bool(measured)), _dp(out)))
+        return out
+
+    def combined_greens_iterator(self, safe_mult, recalculate=None, start=0, stop=None, fetch=True):
+        """CombinedGreensIterator (greens_iterators.jl:154-435): yields (l, G0l, Gl0, Gll), each
+        (N, N, nb, B); with fetch=False the matrices stay on the device and None is yielded instead."""
+        recalculate = 2 * int(safe_mult) if recalculate is None else int(recalculate)
+        stop = self.M if stop is None else int(stop)
+        self._ck(self._L.dqmc_cgi_begin(self._h, recalculate, int(start), stop, int(safe_mult)))
+        l = C.c_int32(0)
+        while True:
+            bufs = [np.zeros(self._gshape(self.B), order="F") for _ in range(3)] if fetch else [None] * 3
+            ptrs = [(_dp(b) if b is not None else None) for b in bufs]
+            self._ck(self._L.dqmc_cgi_next(self._h, C.byref(l), *ptrs))
+            if l.value < 0:
+                return
+            yield (l.value, *bufs)
+
     # ------------------------------------------------------------------ observables
     def accumulate_greens(self):
         self._ck(self._L.dqmc_accumulate_greens(self._h))

@@ -16,95 +16,19 @@
 #include <string>
 #include <vector>
 
-#include "../../include/dqmc_b200.h"
-#include "common.cuh"
-
-using namespace dqmc;
+#include "ctx.cuh"
 
 namespace dqmc { long long g_kernel_launches = 0; }
 
 static thread_local std::string g_create_error;
 
-struct dqmc_ctx {
-    int N = 0, M = 0, nb = 1, kind = 0, B = 0, C = 0;
-    std::vector<int> rfirst, rlast;
-    double alpha = 0.0;
-    int check_sign = 1, check_prop = 1;
-    unsigned long long seed = 0; long long chain_offset = 0; int device = 0; int kb = 0;
-    int ld = 0; long long ms = 0; int nmat = 0; int ldv = 0;
-    cudaStream_t st = nullptr;
-    // device state
-    double *eT2 = nullptr, *eT2i = nullptr, *eTh = nullptr, *eThi = nullptr;
-    int8_t* conf = nullptr;
-    double *u_stack = nullptr, *d_stack = nullptr, *t_stack = nullptr;
-    double *greens = nullptr, *greens_temp = nullptr, *Ul = nullptr, *Ur = nullptr, *Tl = nullptr, *Tr = nullptr;
-    double *tmp1 = nullptr, *tmp2 = nullptr, *curr_U = nullptr, *Dl = nullptr, *Dr = nullptr;
-    double *Vwork = nullptr, *tau = nullptr, *udt_scratch = nullptr;
-    int* pivot = nullptr; int* udt_iscratch = nullptr;
-    int* accepted = nullptr;
-    double *stats_neg = nullptr, *stats_prop = nullptr;
-    double* obs = nullptr; long long obs_len = 0;
-    double* d_uniforms = nullptr; unsigned char* d_forced = nullptr; double* d_probs = nullptr;
-    unsigned char* d_dec = nullptr;
-    double* h_stage = nullptr; size_t h_stage_bytes = 0;
-    // stack state (stack.jl:50-52)
-    int current_slice = 0, current_range = 1, direction = 1;
-    long long sweep_index = 0;
-    std::string err;
-    std::vector<void*> allocs;
-    // per-category CUDA-event profiler
-    bool prof_on = false; int prof_depth = 0;
-    std::vector<cudaEvent_t> prof_pool; size_t prof_used = 0;
-    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_spans;
-};
-
-static cudaEvent_t prof_event(dqmc_ctx* c)
-{
-    if (c->prof_used == c->prof_pool.size()) {
-        cudaEvent_t e; cudaEventCreate(&e); c->prof_pool.push_back(e);
-    }
-    return c->prof_pool[c->prof_used++];
-}
-// times the outermost category only (rdivp! contains GEMM launches of its own)
-struct ProfScope {
-    dqmc_ctx* c; cudaEvent_t e1 = nullptr; bool active;
-    ProfScope(dqmc_ctx* ctx, int cat) : c(ctx), active(ctx->prof_on && ctx->prof_depth == 0)
-    {
-        ++c->prof_depth;
-        if (active) {
-            cudaEvent_t e0 = prof_event(c); e1 = prof_event(c);
-            cudaEventRecord(e0, c->st);
-            c->prof_spans.push_back({cat, {e0, e1}});
-        }
-    }
-    ~ProfScope() { --c->prof_depth; if (active) cudaEventRecord(e1, c->st); }
-};
-
-#define FAIL(ctx, code, msg) do { (ctx)->err = (msg); return (code); } while (0)
-#define CK(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
-    (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__); return DQMC_ERR_CUDA; } } while (0)
-
-template <class T> static cudaError_t dalloc(dqmc_ctx* c, T** p, size_t count)
-{
-    void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(q, 0, (count ? count : 1) * sizeof(T), c->st);
-    c->allocs.push_back(q);
-    *p = (T*)q;
-    return e;
-}
-
-static inline double* slot_mat(dqmc_ctx* c, double* base, int slot) { return base + (long long)slot * c->nmat * c->ms; }
-static inline double* slot_vec(dqmc_ctx* c, double* base, int slot) { return base + (long long)slot * c->nmat * c->N; }
-
 // ---- host <-> device matrix copies (host ld = N, device ld = c->ld) ------------------------
-static cudaError_t h2d_mats(dqmc_ctx* c, double* dst, const double* src, long long nmats)
+cudaError_t h2d_mats(dqmc_ctx* c, double* dst, const double* src, long long nmats)
 {
     return cudaMemcpy2DAsync(dst, (size_t)c->ld * 8, src, (size_t)c->N * 8, (size_t)c->N * 8,
                              (size_t)c->N * nmats, cudaMemcpyHostToDevice, c->st);
 }
-static cudaError_t d2h_mats(dqmc_ctx* c, double* dst, const double* src, long long nmats)
+cudaError_t d2h_mats(dqmc_ctx* c, double* dst, const double* src, long long nmats)
 {
     return cudaMemcpy2DAsync(dst, (size_t)c->N * 8, src, (size_t)c->ld * 8, (size_t)c->N * 8,
                              (size_t)c->N * nmats, cudaMemcpyDeviceToHost, c->st);
@@ -112,7 +36,7 @@ static cudaError_t d2h_mats(dqmc_ctx* c, double* dst, const double* src, long lo
 
 // ---- fused diagonal factors ------------------------------------------------------------------
 // interaction_matrix_exp!(..., slice, power) (fields.jl:380-386, 429-438) as a Scale
-static Scale field_scale(dqmc_ctx* c, int slice, double power)
+Scale field_scale(dqmc_ctx* c, int slice, double power)
 {
     Scale s{};
     s.mode = 3;
@@ -122,12 +46,12 @@ static Scale field_scale(dqmc_ctx* c, int slice, double power)
     s.nb = c->nb; s.flip = (c->kind == DQMC_FIELD_MAGNETIC_HIRSCH) ? 1 : 0;
     return s;
 }
-static Scale vec_scale(dqmc_ctx* c, const double* v, bool inverse = false)
+Scale vec_scale(dqmc_ctx* c, const double* v, bool inverse)
 {
     Scale s{}; s.mode = inverse ? 2 : 1; s.vec = v; s.stride = c->N; s.nb = c->nb; return s;
 }
 
-static GemmParams gemm_base(dqmc_ctx* c)
+GemmParams gemm_base(dqmc_ctx* c)
 {
     GemmParams g{};
     g.M = g.N = g.K = c->N;
@@ -140,9 +64,8 @@ static GemmParams gemm_base(dqmc_ctx* c)
 }
 
 // dst = op(A) * op(B) with optional fused factors
-static cudaError_t mm(dqmc_ctx* c, double* dst, const double* A, bool tA, bool sharedA, const double* Bm, bool tB,
-                      bool sharedB, Scale rs = no_scale(), Scale ks = no_scale(), Scale cs = no_scale(),
-                      const double* add_diag = nullptr)
+cudaError_t mm(dqmc_ctx* c, double* dst, const double* A, bool tA, bool sharedA, const double* Bm, bool tB,
+                      bool sharedB, Scale rs, Scale ks, Scale cs, const double* add_diag, double alpha, double beta)
 {
     ProfScope ps(c, DQMC_PROF_GEMM);
     GemmParams g = gemm_base(c);
@@ -150,23 +73,24 @@ static cudaError_t mm(dqmc_ctx* c, double* dst, const double* A, bool tA, bool s
     g.B = Bm; g.transB = tB; if (sharedB) g.strideB = 0;
     g.C = dst; g.rs = rs; g.ks = ks; g.cs = cs;
     g.add_diag = add_diag; g.add_stride = c->N;
+    g.alpha = alpha; g.beta = beta;
     return launch_gemm(g, c->st);
 }
 
 // stack.jl:319-367, out of place
-static cudaError_t slice_left(dqmc_ctx* c, double* dst, const double* src, int slice)        // eT2 * eV * M
+cudaError_t slice_left(dqmc_ctx* c, double* dst, const double* src, int slice)        // eT2 * eV * M
 { return mm(c, dst, c->eT2, false, true, src, false, false, no_scale(), field_scale(c, slice, 1.0)); }
-static cudaError_t slice_right(dqmc_ctx* c, double* dst, const double* src, int slice)       // M * eT2 * eV
+cudaError_t slice_right(dqmc_ctx* c, double* dst, const double* src, int slice)       // M * eT2 * eV
 { return mm(c, dst, src, false, false, c->eT2, false, true, no_scale(), no_scale(), field_scale(c, slice, 1.0)); }
-static cudaError_t slice_inv_right(dqmc_ctx* c, double* dst, const double* src, int slice)   // M * eV^-1 * eT2^-1
+cudaError_t slice_inv_right(dqmc_ctx* c, double* dst, const double* src, int slice)   // M * eV^-1 * eT2^-1
 { return mm(c, dst, src, false, false, c->eT2i, false, true, no_scale(), field_scale(c, slice, -1.0)); }
-static cudaError_t slice_inv_left(dqmc_ctx* c, double* dst, const double* src, int slice)    // eV^-1 * eT2^-1 * M
+cudaError_t slice_inv_left(dqmc_ctx* c, double* dst, const double* src, int slice)    // eV^-1 * eT2^-1 * M
 { return mm(c, dst, c->eT2i, false, true, src, false, false, field_scale(c, slice, -1.0)); }
-static cudaError_t slice_daggered_left(dqmc_ctx* c, double* dst, const double* src, int slice) // eV' * eT2' * M
+cudaError_t slice_daggered_left(dqmc_ctx* c, double* dst, const double* src, int slice) // eV' * eT2' * M
 { return mm(c, dst, c->eT2, true, true, src, false, false, field_scale(c, slice, 1.0)); }
 
 // wrap_greens! (stack.jl:594-603): gf -> tmp -> gf
-static cudaError_t wrap_greens(dqmc_ctx* c, double* gf, double* tmp, int curr_slice, int direction)
+cudaError_t wrap_greens(dqmc_ctx* c, double* gf, double* tmp, int curr_slice, int direction)
 {
     cudaError_t e;
     if (direction == -1) {
@@ -177,7 +101,7 @@ static cudaError_t wrap_greens(dqmc_ctx* c, double* gf, double* tmp, int curr_sl
     return slice_inv_right(c, gf, tmp, curr_slice);
 }
 
-static cudaError_t udt(dqmc_ctx* c, const double* A, Scale colscale, double* U, double* D, double* T, bool apply_pivot)
+cudaError_t udt(dqmc_ctx* c, const double* A, Scale colscale, double* U, double* D, double* T, bool apply_pivot)
 {
     ProfScope ps(c, DQMC_PROF_UDT);
     UdtParams p{};
@@ -190,7 +114,7 @@ static cudaError_t udt(dqmc_ctx* c, const double* A, Scale colscale, double* U, 
     return launch_udt(p, c->st);
 }
 
-static cudaError_t rdivp(dqmc_ctx* c, double* A, const double* T, double* work)
+cudaError_t rdivp(dqmc_ctx* c, double* A, const double* T, double* work)
 {
     ProfScope ps(c, DQMC_PROF_RDIVP);
     RdivpParams p{};
@@ -200,14 +124,13 @@ static cudaError_t rdivp(dqmc_ctx* c, double* A, const double* T, double* work)
     return launch_rdivp(p, c->st);
 }
 
-static cudaError_t copy_mats(dqmc_ctx* c, double* dst, const double* src)
+cudaError_t copy_mats(dqmc_ctx* c, double* dst, const double* src)
 { ProfScope ps(c, DQMC_PROF_OTHER); return cudaMemcpyAsync(dst, src, (size_t)c->nmat * c->ms * 8, cudaMemcpyDeviceToDevice, c->st); }
-static cudaError_t copy_vecs(dqmc_ctx* c, double* dst, const double* src)
+cudaError_t copy_vecs(dqmc_ctx* c, double* dst, const double* src)
 { ProfScope ps(c, DQMC_PROF_OTHER); return cudaMemcpyAsync(dst, src, (size_t)c->nmat * c->N * 8, cudaMemcpyDeviceToDevice, c->st); }
-static cudaError_t ident(dqmc_ctx* c, double* A) { ProfScope ps(c, DQMC_PROF_OTHER); return launch_set_identity(A, c->N, c->ld, c->ms, c->nmat, c->st); }
-static cudaError_t ones(dqmc_ctx* c, double* v) { ProfScope ps(c, DQMC_PROF_OTHER); return launch_fill(v, 1.0, (long long)c->nmat * c->N, c->st); }
+cudaError_t ident(dqmc_ctx* c, double* A) { ProfScope ps(c, DQMC_PROF_OTHER); return launch_set_identity(A, c->N, c->ld, c->ms, c->nmat, c->st); }
+cudaError_t ones(dqmc_ctx* c, double* v) { ProfScope ps(c, DQMC_PROF_OTHER); return launch_fill(v, 1.0, (long long)c->nmat * c->N, c->st); }
 
-#define CE(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return e__; } while (0)
 
 // calculate_greens_AVX! (stack.jl:442-496); destroys Ul, Dl, Tl, Ur, Dr, Tr like the reference.
 static cudaError_t calculate_greens(dqmc_ctx* c, double* G)
@@ -365,6 +288,7 @@ static cudaError_t sweep_spatial(dqmc_ctx* c, int step, const double* d_unif, lo
     p.accepted = c->accepted; p.stats = c->stats_neg;
     p.forced = d_forced; p.probs = d_probs; p.decisions = d_dec; p.tstride = tstride;
     p.kb = c->kb;
+    c->generation += 1;
     return launch_update(p, c->st);
 }
 
@@ -413,6 +337,7 @@ int32_t dqmc_destroy(dqmc_ctx* c)
     if (!c) return DQMC_OK;
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
+    ut_destroy(c);
     for (void* p : c->allocs) cudaFree(p);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -511,8 +436,6 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     return DQMC_OK;
 }
 
-#define ENTER(c) do { if (!(c)) return DQMC_ERR_INVALID; cudaSetDevice((c)->device); } while (0)
-#define CHAINS_OK(c, c0, nc) ((c0) >= 0 && (nc) >= 0 && (c0) + (nc) <= (c)->B)
 
 int32_t dqmc_set_conf(dqmc_ctx* c, int32_t chain0, int32_t nchains, const int8_t* conf)
 {
@@ -521,6 +444,7 @@ int32_t dqmc_set_conf(dqmc_ctx* c, int32_t chain0, int32_t nchains, const int8_t
     const size_t per = (size_t)c->M * c->N;
     for (size_t i = 0; i < per * nchains; ++i)
         if (conf[i] != 1 && conf[i] != -1) FAIL(c, DQMC_ERR_INVALID, "dqmc_set_conf: conf values must be +-1");
+    c->generation += 1;
     CK(c, cudaMemcpyAsync(c->conf + per * chain0, conf, per * nchains, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaStreamSynchronize(c->st));
     return DQMC_OK;

@@ -17,7 +17,8 @@ extern long long g_kernel_launches;   // kernels launched by this library (instr
 // interaction_matrix_exp! (reference src/flavors/DQMC/fields.jl:380-386, 429-438)
 // on the fly from the Int8 HS field: exp(+-alpha) chosen by the sign of conf.
 struct Scale {
-    int mode;            // 0 none, 1 vec[i], 2 1/vec[i], 3 field
+    int mode;            // 0 none, 1 vec[i], 2 1/vec[i], 3 field, 4 min(1, vec[i]), 5 1/max(1, vec[i])
+                         // (4, 5: vmin! / vmaxinv!, reference linalg/real.jl:137-164)
     const double* vec;   // mode 1/2: base pointer, matrix m uses vec + m * stride
     long long stride;
     const int8_t* conf;  // mode 3: conf + chain * cstride + i  (already offset to the slice)
@@ -33,6 +34,8 @@ __device__ __forceinline__ double scale_at(const Scale& s, int m, int i)
 {
     if (s.mode == 1) return s.vec[(long long)m * s.stride + i];
     if (s.mode == 2) return 1.0 / s.vec[(long long)m * s.stride + i];
+    if (s.mode == 4) return fmin(1.0, s.vec[(long long)m * s.stride + i]);
+    if (s.mode == 5) return 1.0 / fmax(1.0, s.vec[(long long)m * s.stride + i]);
     const int chain = m / s.nb, blk = m - chain * s.nb;
     const bool up = s.conf[(long long)chain * s.cstride + i] > 0;
     const bool sw = (s.flip != 0) && (blk == 1);
@@ -113,5 +116,8 @@ cudaError_t launch_permute_cols(const double* A, double* O, const int* pivot, in
 cudaError_t launch_prop_error(const double* A, const double* B, int n, int ld, long long stride_chain,
                               int nb, int n_chains, double thresh, double* stats, cudaStream_t st);
 cudaError_t launch_accumulate(const double* G, double* sum, double* sumsq, long long count, cudaStream_t st);
+// O = diag(rs) * A * diag(cs) + add (add may be null; O may alias A or add); A == nullptr means the identity
+cudaError_t launch_scale_add(double* O, const double* A, Scale rs, Scale cs, const double* add, double add_diag,
+                             int n, int ld, long long stride, int batch, cudaStream_t st);
 
 }  // namespace dqmc

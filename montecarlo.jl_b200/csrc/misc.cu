@@ -120,4 +120,39 @@ cudaError_t launch_accumulate(const double* G, double* sum, double* sumsq, long 
     return cudaGetLastError();
 }
 
+// O = diag(rs) * A * diag(cs) + add + add_diag * I.  A == nullptr stands for the identity, which gives
+// copyto!(O, Diagonal(d)) (unequal_time_stack.jl:597, 679); add_diag = -1 with unit scales is
+// vsub!(O, A, I) (linalg/real.jl:122-132); add != nullptr is rvadd! (:117-121).
+__global__ void scale_add_kernel(double* O, const double* A, Scale rs, Scale cs, const double* add, double add_diag,
+                                 int n, int ld, long long stride)
+{
+    const int mat = blockIdx.y;
+    const long long off = (long long)mat * stride;
+    const long long tot = (long long)ld * n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % ld), j = (int)(e / ld);
+        if (i >= n) continue;
+        double v = A ? A[off + e] : ((i == j) ? 1.0 : 0.0);
+        if (v != 0.0 || A) {
+            if (rs.mode) v *= scale_at(rs, mat, i);
+            if (cs.mode) v *= scale_at(cs, mat, j);
+        }
+        if (add) v += add[off + e];
+        if (i == j) v += add_diag;
+        O[off + e] = v;
+    }
+}
+
+cudaError_t launch_scale_add(double* O, const double* A, Scale rs, Scale cs, const double* add, double add_diag,
+                             int n, int ld, long long stride, int batch, cudaStream_t st)
+{
+    if (batch <= 0) return cudaSuccess;
+    const long long tot = (long long)ld * n;
+    dim3 grid((unsigned)((tot + 255) / 256 > 64 ? 64 : (tot + 255) / 256), (unsigned)batch);
+    scale_add_kernel<<<grid, 256, 0, st>>>(O, A, rs, cs, add, add_diag, n, ld, stride);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
 }  // namespace dqmc

@@ -1,0 +1,506 @@
+// ut.cu -- unequal-time Green's functions on the device: UnequalTimeStack, greens(mc, k, l) and the
+// CombinedGreensIterator behind TimeIntegral measurements.
+//
+// Reference (paths relative to /root/reference):
+//   src/flavors/DQMC/unequal_time_stack.jl   build_stack :128-185, lazy_build_* :187-300,
+//       calculate_greens(mc, k, l) :322-335, _find_range_with_value :353-384,
+//       compute_inverse/forward/backward_udt_block! :400-533, calculate_greens_full1!/2! :537-697
+//   src/flavors/DQMC/measurements/greens_iterators.jl   CombinedGreensIterator :154-435
+//
+// Same state machine and the same matrix algebra as the reference, batched over all chains x flavor
+// blocks, built from the library's three device kernels (DMMA GEMM with fused diagonal factors,
+// column-pivoted QR, rdivp).  What differs from a transliteration:
+//   * every Diagonal factor (D, 1/D, min(1, D), 1/max(1, D), exp(+-alpha x)) rides in a GEMM prologue /
+//     epilogue or in the QR load (Scale modes of common.cuh); vmin!/vmaxinv!/vinv! never run as passes,
+//   * the reference's in-place products become out-of-place GEMMs into a scratch matrix followed by a
+//     pointer swap, so nothing is copied,
+//   * sums of two scaled products (full1 "B3 + B4") are one GEMM accumulating into the other's output.
+// The iterator's outputs stay on the device (for the Wick kernels of measure.cu) unless the caller
+// passes host buffers.
+#include <algorithm>
+
+#include "ctx.cuh"
+
+struct dqmc_ut {
+    // B_{idx sm} ... B_1 ; (B_M ... B_{idx sm + 1})^T ; B^-1 blocks (unequal_time_stack.jl:1-19)
+    double *fu = nullptr, *fd = nullptr, *ft = nullptr;     // C + 1 slots
+    double *bu = nullptr, *bd = nullptr, *bt = nullptr;     // C + 1 slots
+    double *iu = nullptr, *id = nullptr, *it = nullptr;     // C slots
+    std::vector<char> inv_done;
+    int forward_idx = 1, backward_idx = 0;                  // 1-based like the reference
+    double *greens = nullptr, *tmp = nullptr, *U = nullptr, *D = nullptr, *T = nullptr;   // :21-26
+    double *s1 = nullptr, *s2 = nullptr, *dv = nullptr;     // scratch (out-of-place products, D copies)
+    long long last_update = -1; int last_k = -1, last_l = -1;
+    // CombinedGreensIterator
+    bool it_active = false; int it_recalc = 0, it_start = 0, it_stop = 0, it_safe_mult = 0, it_next = 0;
+    const double *out_G0l = nullptr, *out_Gl0 = nullptr, *out_Gll = nullptr;
+};
+
+void ut_destroy(dqmc_ctx* c) { delete c->ut; c->ut = nullptr; }   // device memory is owned by c->allocs
+
+static inline double* umat(dqmc_ctx* c, double* base, int slot) { return base + (long long)slot * c->nmat * c->ms; }
+static inline double* uvec(dqmc_ctx* c, double* base, int slot) { return base + (long long)slot * c->nmat * c->N; }
+
+static Scale vmin_scale(dqmc_ctx* c, const double* v) { Scale s = vec_scale(c, v); s.mode = 4; return s; }
+static Scale vmaxinv_scale(dqmc_ctx* c, const double* v) { Scale s = vec_scale(c, v); s.mode = 5; return s; }
+
+static cudaError_t scale_add(dqmc_ctx* c, double* O, const double* A, Scale rs, Scale cs, const double* add,
+                             double add_diag)
+{
+    ProfScope ps(c, DQMC_PROF_OTHER);
+    return launch_scale_add(O, A, rs, cs, add, add_diag, c->N, c->ld, c->ms, c->nmat, c->st);
+}
+
+// plain product dst = op(A) op(B)
+static cudaError_t mul(dqmc_ctx* c, double* dst, const double* A, bool tA, const double* B, bool tB,
+                       Scale rs = no_scale(), Scale ks = no_scale(), Scale cs = no_scale(), double alpha = 1.0,
+                       double beta = 0.0)
+{ return mm(c, dst, A, tA, false, B, tB, false, rs, ks, cs, nullptr, alpha, beta); }
+
+// _greens! (greens.jl:114-125): target = eThalf^-1 (source eThalf); target may alias source
+static cudaError_t measured_into(dqmc_ctx* c, double* target, const double* source, double* temp)
+{
+    CE(mm(c, temp, source, false, false, c->eTh, false, true));
+    return mm(c, target, c->eThi, false, true, temp, false, false);
+}
+
+// unequal_time_stack.jl:60-118
+static cudaError_t ut_get(dqmc_ctx* c, dqmc_ut** out)
+{
+    if (c->ut) { *out = c->ut; return cudaSuccess; }
+    dqmc_ut* u = new dqmc_ut();
+    c->ut = u;
+    const size_t mat = (size_t)c->nmat * c->ms, vec = (size_t)c->nmat * c->N;
+    const int E = c->C + 1;
+    CE(dalloc(c, &u->fu, mat * E)); CE(dalloc(c, &u->fd, vec * E)); CE(dalloc(c, &u->ft, mat * E));
+    CE(dalloc(c, &u->bu, mat * E)); CE(dalloc(c, &u->bd, vec * E)); CE(dalloc(c, &u->bt, mat * E));
+    CE(dalloc(c, &u->iu, mat * c->C)); CE(dalloc(c, &u->id, vec * c->C)); CE(dalloc(c, &u->it, mat * c->C));
+    CE(dalloc(c, &u->greens, mat)); CE(dalloc(c, &u->tmp, mat)); CE(dalloc(c, &u->U, mat)); CE(dalloc(c, &u->T, mat));
+    CE(dalloc(c, &u->s1, mat)); CE(dalloc(c, &u->s2, mat));
+    CE(dalloc(c, &u->D, vec)); CE(dalloc(c, &u->dv, vec));
+    u->inv_done.assign((size_t)c->C, 0);
+    u->forward_idx = 1; u->backward_idx = E - 1;
+    CE(ident(c, umat(c, u->fu, 0))); CE(ones(c, uvec(c, u->fd, 0))); CE(ident(c, umat(c, u->ft, 0)));
+    CE(ident(c, umat(c, u->bu, E - 1))); CE(ones(c, uvec(c, u->bd, E - 1))); CE(ident(c, umat(c, u->bt, E - 1)));
+    *out = u;
+    return cudaSuccess;
+}
+
+// ---- one range of the three builds; idx = 1-based range index --------------------------------------
+static cudaError_t ut_forward_step(dqmc_ctx* c, dqmc_ut* u, int idx)        // :132-143
+{
+    const double* src = umat(c, u->fu, idx - 1);
+    double* bufs[2] = {c->curr_U, c->tmp2};
+    int w = 0;
+    for (int s = c->rfirst[idx - 1]; s <= c->rlast[idx - 1]; ++s) { CE(slice_left(c, bufs[w], src, s)); src = bufs[w]; w ^= 1; }
+    CE(udt(c, src, vec_scale(c, uvec(c, u->fd, idx - 1)), umat(c, u->fu, idx), uvec(c, u->fd, idx), c->tmp1, true));
+    return mul(c, umat(c, u->ft, idx), c->tmp1, false, umat(c, u->ft, idx - 1), false);
+}
+static cudaError_t ut_backward_step(dqmc_ctx* c, dqmc_ut* u, int idx)       // :148-159
+{
+    const double* src = umat(c, u->bu, idx);
+    double* bufs[2] = {c->curr_U, c->tmp2};
+    int w = 0;
+    for (int s = c->rlast[idx - 1]; s >= c->rfirst[idx - 1]; --s) { CE(slice_daggered_left(c, bufs[w], src, s)); src = bufs[w]; w ^= 1; }
+    CE(udt(c, src, vec_scale(c, uvec(c, u->bd, idx)), umat(c, u->bu, idx - 1), uvec(c, u->bd, idx - 1), c->tmp1, true));
+    return mul(c, umat(c, u->bt, idx - 1), c->tmp1, false, umat(c, u->bt, idx), false);
+}
+static cudaError_t ut_inv_step(dqmc_ctx* c, dqmc_ut* u, int idx)            // :165-174
+{
+    double* bufs[2] = {c->curr_U, c->tmp2};
+    CE(ident(c, bufs[0]));
+    const double* src = bufs[0];
+    int w = 1;
+    for (int s = c->rlast[idx - 1]; s >= c->rfirst[idx - 1]; --s) { CE(slice_inv_left(c, bufs[w], src, s)); src = bufs[w]; w ^= 1; }
+    return udt(c, src, no_scale(), umat(c, u->iu, idx - 1), uvec(c, u->id, idx - 1), umat(c, u->it, idx - 1), true);
+}
+
+static cudaError_t ut_build_stack(dqmc_ctx* c, dqmc_ut* u)                  // :128-185
+{
+    for (int idx = 1; idx <= c->C; ++idx) CE(ut_forward_step(c, u, idx));
+    for (int idx = c->C; idx >= 1; --idx) CE(ut_backward_step(c, u, idx));
+    for (int idx = 1; idx <= c->C; ++idx) { CE(ut_inv_step(c, u, idx)); u->inv_done[idx - 1] = 1; }
+    u->forward_idx = c->C + 1; u->backward_idx = 1;
+    u->last_update = c->generation; u->last_k = u->last_l = -1;
+    return cudaSuccess;
+}
+
+static void ut_lazy_reset(dqmc_ctx* c, dqmc_ut* u)                          // :209-214
+{
+    if (u->last_update != c->generation) {
+        u->last_update = c->generation;
+        std::fill(u->inv_done.begin(), u->inv_done.end(), 0);
+        u->forward_idx = 1; u->backward_idx = c->C + 1;
+    }
+}
+static cudaError_t ut_lazy_build_forward(dqmc_ctx* c, dqmc_ut* u, int upto)
+{
+    ut_lazy_reset(c, u);
+    for (int idx = u->forward_idx; idx <= upto - 1; ++idx) CE(ut_forward_step(c, u, idx));
+    u->forward_idx = std::max(upto, u->forward_idx);
+    return cudaSuccess;
+}
+static cudaError_t ut_lazy_build_backward(dqmc_ctx* c, dqmc_ut* u, int downto)
+{
+    ut_lazy_reset(c, u);
+    for (int idx = u->backward_idx - 1; idx >= downto; --idx) CE(ut_backward_step(c, u, idx));
+    u->backward_idx = std::min(downto, u->backward_idx);
+    return cudaSuccess;
+}
+static cudaError_t ut_lazy_build_inv(dqmc_ctx* c, dqmc_ut* u, int from, int to)
+{
+    ut_lazy_reset(c, u);
+    for (int idx = from; idx <= to; ++idx) {
+        if (u->inv_done[idx - 1]) continue;
+        u->inv_done[idx - 1] = 1;
+        CE(ut_inv_step(c, u, idx));
+    }
+    return cudaSuccess;
+}
+
+// :353-384
+static int find_range_with_value(const dqmc_ctx* c, int val)
+{
+    if (val < 1) return 0;
+    if (val > c->rlast[c->C - 1]) return c->C + 1;
+    for (int i = 0; i < c->C; ++i) if (c->rfirst[i] <= val && val <= c->rlast[i]) return i + 1;
+    return c->C + 1;
+}
+
+// :400-457   u->U u->D u->T = B_{low+1}^-1 ... B_high^-1
+static cudaError_t compute_inverse_udt_block(dqmc_ctx* c, dqmc_ut* u, int low, int high)
+{
+    const int lower = find_range_with_value(c, low) + 1;
+    const int upper = find_range_with_value(c, high + 1) - 1;
+    CE(ut_lazy_build_inv(c, u, lower, upper));
+    CE(ident(c, u->U)); CE(ones(c, u->D)); CE(ident(c, u->T));
+    for (int idx = lower; idx <= upper; ++idx) {
+        // tmp1 = Diagonal(D) (T inv_u) Diagonal(inv_d); tmp2, D, tmp1 = udt(tmp1)
+        CE(mul(c, c->tmp1, u->T, false, umat(c, u->iu, idx - 1), false, vec_scale(c, u->D), no_scale(),
+               vec_scale(c, uvec(c, u->id, idx - 1))));
+        CE(udt(c, c->tmp1, no_scale(), c->tmp2, u->D, c->tmp1, true));
+        CE(mul(c, u->s1, c->tmp1, false, umat(c, u->it, idx - 1), false)); std::swap(u->T, u->s1);
+        CE(mul(c, u->s1, u->U, false, c->tmp2, false)); std::swap(u->U, u->s1);
+    }
+    const int lower_slice = (lower <= c->C) ? c->rfirst[lower - 1] : c->rlast[c->C - 1] + 1;
+    const int upper_slice = (upper > 0) ? c->rlast[upper - 1] : 0;
+    const int top = std::min(lower_slice - 1, high);
+    for (int s = top; s >= low + 1; --s) { CE(slice_inv_left(c, u->s1, u->U, s)); std::swap(u->U, u->s1); }
+    if (top >= low + 1) {
+        CE(copy_vecs(c, u->dv, u->D));
+        CE(udt(c, u->U, vec_scale(c, u->dv), u->s1, u->D, c->tmp1, true)); std::swap(u->U, u->s1);
+        CE(mul(c, u->s1, c->tmp1, false, u->T, false)); std::swap(u->T, u->s1);
+    }
+    for (int s = std::max(upper_slice + 1, top + 1); s <= high; ++s) { CE(slice_inv_right(c, u->s1, u->T, s)); std::swap(u->T, u->s1); }
+    return cudaSuccess;
+}
+
+// :472-494   Ul Dl Tl = B_slice ... B_1
+static cudaError_t compute_forward_udt_block(dqmc_ctx* c, dqmc_ut* u, int slice)
+{
+    const int idx = std::max(0, find_range_with_value(c, slice) - 1);
+    CE(ut_lazy_build_forward(c, u, idx + 1));
+    const double* src = umat(c, u->fu, idx);
+    double* bufs[2] = {c->Tl, u->s1};
+    int w = 0;
+    const int target = (idx > 0) ? c->rlast[idx - 1] + 1 : 1;
+    for (int l = target; l <= slice; ++l) { CE(slice_left(c, bufs[w], src, l)); src = bufs[w]; w ^= 1; }
+    CE(udt(c, src, vec_scale(c, uvec(c, u->fd, idx)), c->Ul, c->Dl, c->tmp1, true));
+    return mul(c, c->Tl, c->tmp1, false, umat(c, u->ft, idx), false);
+}
+
+// :509-533   (Ur Dr Tr)^T = B_M ... B_{slice+1}
+static cudaError_t compute_backward_udt_block(dqmc_ctx* c, dqmc_ut* u, int slice)
+{
+    const int idx = find_range_with_value(c, slice) + 1;
+    CE(ut_lazy_build_backward(c, u, idx));
+    const double* src = umat(c, u->bu, idx - 1);
+    double* bufs[2] = {c->Tr, u->s1};
+    int w = 0;
+    const int target = (idx <= c->C) ? c->rfirst[idx - 1] - 1 : c->rlast[c->C - 1];
+    for (int l = target; l >= slice + 1; --l) { CE(slice_daggered_left(c, bufs[w], src, l)); src = bufs[w]; w ^= 1; }
+    CE(udt(c, src, vec_scale(c, uvec(c, u->bd, idx - 1)), c->Ur, c->Dr, c->tmp1, true));
+    return mul(c, c->Tr, c->tmp1, false, umat(c, u->bt, idx - 1), false);
+}
+
+// :537-618   slice1 >= slice2:  G = [U D T + Ul Dl Tl Tr' Dr Ur']^-1
+static cudaError_t calculate_greens_full1(dqmc_ctx* c, dqmc_ut* u, int slice1, int slice2)
+{
+    CE(compute_inverse_udt_block(c, u, slice2, slice1));
+    CE(compute_forward_udt_block(c, u, slice2));
+    CE(compute_backward_udt_block(c, u, slice1));
+    // B1: greens = Dl (Tl Tr') Dr; Tr, Dr, greens = udt(greens), unpivoted form
+    CE(mul(c, u->greens, c->Tl, false, c->Tr, true, vec_scale(c, c->Dl), no_scale(), vec_scale(c, c->Dr)));
+    CE(udt(c, u->greens, no_scale(), c->Tr, c->Dr, u->greens, false));
+    // B2: Tl = Ul Tr; Ur = Ur / greens
+    CE(mul(c, c->Tl, c->Ul, false, c->Tr, false));
+    CE(rdivp(c, c->Ur, u->greens, c->Ul));
+    // B4 + B3: tmp1 = min(1,D) (T Ur) / max(1,Dr)  +  1/max(1,D) (U' Tl) min(1,Dr)
+    CE(mul(c, c->tmp1, u->T, false, c->Ur, false, vmin_scale(c, u->D), no_scale(), vmaxinv_scale(c, c->Dr)));
+    CE(mul(c, c->tmp1, u->U, true, c->Tl, false, vmaxinv_scale(c, u->D), no_scale(), vmin_scale(c, c->Dr), 1.0, 1.0));
+    // Tr, Dl, Tl = udt(sum), unpivoted form
+    CE(udt(c, c->tmp1, no_scale(), c->Tr, c->Dl, c->Tl, false));
+    // B5: greens = {[(1/max(1,Dr)) / Tl] 1/Dl} Tr' / max(1,D)
+    CE(scale_add(c, c->Ul, nullptr, vmaxinv_scale(c, c->Dr), no_scale(), nullptr, 0.0));
+    CE(rdivp(c, c->Ul, c->Tl, c->tmp1));
+    CE(mul(c, u->greens, c->Ul, false, c->Tr, true, no_scale(), vec_scale(c, c->Dl, true), vmaxinv_scale(c, u->D)));
+    // B6: greens = Ur (greens U')
+    CE(mul(c, c->Tr, u->greens, false, u->U, true));
+    return mul(c, u->greens, c->Ur, false, c->Tr, false);
+}
+
+// :621-697   slice1 <= slice2:  G = -[T^-1 D^-1 U' + Ur (Dl Tl Tr' Dr)^-1 Ul']^-1
+static cudaError_t calculate_greens_full2(dqmc_ctx* c, dqmc_ut* u, int slice1, int slice2)
+{
+    CE(compute_inverse_udt_block(c, u, slice1, slice2));
+    CE(compute_forward_udt_block(c, u, slice1));
+    CE(compute_backward_udt_block(c, u, slice2));
+    // B1
+    CE(mul(c, u->greens, c->Tl, false, c->Tr, true, vec_scale(c, c->Dl), no_scale(), vec_scale(c, c->Dr)));
+    CE(udt(c, u->greens, no_scale(), c->Tr, c->Dr, u->greens, false));
+    // B2: Tl = Ul Tr (kept); Ul = 1/max(1,D) (U' Tl) min(1,Dr)
+    CE(mul(c, c->Tl, c->Ul, false, c->Tr, false));
+    CE(mul(c, c->Ul, u->U, true, c->Tl, false, vmaxinv_scale(c, u->D), no_scale(), vmin_scale(c, c->Dr)));
+    // B3: U = (T Ur) / greens; Tr = min(1,D) U / max(1,Dr) + Ul
+    CE(mul(c, u->U, u->T, false, c->Ur, false));
+    CE(rdivp(c, u->U, u->greens, c->Ur));
+    CE(scale_add(c, c->Tr, u->U, vmin_scale(c, u->D), vmaxinv_scale(c, c->Dr), c->Ul, 0.0));
+    // Ul, Dl, Tr = udt(Tr), unpivoted form
+    CE(udt(c, c->Tr, no_scale(), c->Ul, c->Dl, c->Tr, false));
+    // B4: Ur = {[(min(1,Dr) / Tr) 1/Dl] Ul'} min(1,D)
+    CE(scale_add(c, u->U, nullptr, vmin_scale(c, c->Dr), no_scale(), nullptr, 0.0));
+    CE(rdivp(c, u->U, c->Tr, c->Ur));
+    CE(mul(c, c->Ur, u->U, false, c->Ul, true, no_scale(), vec_scale(c, c->Dl, true), vmin_scale(c, u->D)));
+    // B6: greens = -Tl (Ur T)
+    CE(mul(c, c->Tr, c->Ur, false, u->T, false));
+    return mul(c, u->greens, c->Tl, false, c->Tr, false, no_scale(), no_scale(), no_scale(), -1.0);
+}
+
+// calculate_greens(mc, slice1, slice2) :322-335
+static cudaError_t ut_calculate_greens(dqmc_ctx* c, dqmc_ut* u, int slice1, int slice2)
+{
+    if (u->last_k != slice1 || u->last_l != slice2 || u->last_update != c->generation) {
+        u->last_k = slice1; u->last_l = slice2;
+        if (slice1 >= slice2) CE(calculate_greens_full1(c, u, slice1, slice2));
+        else CE(calculate_greens_full2(c, u, slice1, slice2));
+    }
+    return cudaSuccess;
+}
+
+// ---- CombinedGreensIterator (greens_iterators.jl:198-435) ------------------------------------------
+// (G0l, Gl0, Gll) of the current iteration live in (stack.tmp2, stack.tmp1, uts.greens) like the reference.
+static void cgi_outputs(dqmc_ctx* c, dqmc_ut* u) { u->out_G0l = c->tmp2; u->out_Gl0 = c->tmp1; u->out_Gll = u->greens; }
+
+// :246-272 / :312-331   full recalculation at l
+static cudaError_t cgi_recalculate(dqmc_ctx* c, dqmc_ut* u, int l)
+{
+    CE(calculate_greens_full1(c, u, l, 0)); std::swap(c->curr_U, u->greens);      // G(l, 0)
+    CE(calculate_greens_full2(c, u, 0, l)); std::swap(u->tmp, u->greens);         // G(0, l)
+    CE(calculate_greens_full1(c, u, l, l)); std::swap(u->T, u->greens);           // G(l, l)
+    CE(measured_into(c, u->greens, u->T, c->tmp2));                               // Gll
+    CE(measured_into(c, c->tmp1, c->curr_U, c->tmp2));                            // Gl0
+    std::swap(c->Tl, c->curr_U);                                                  // Tl <- G(l, 0); curr_U is scratch again
+    CE(measured_into(c, c->tmp2, u->tmp, c->curr_U));                             // G0l
+    std::swap(c->Tr, u->tmp);                                                     // Tr <- G(0, l)
+    CE(udt(c, u->T, no_scale(), u->U, u->D, u->T, true));
+    CE(udt(c, c->Tl, no_scale(), c->Ul, c->Dl, c->Tl, true));
+    CE(udt(c, c->Tr, no_scale(), c->Ur, c->Dr, c->Tr, true));
+    cgi_outputs(c, u);
+    return cudaSuccess;
+}
+
+static cudaError_t cgi_advance(dqmc_ctx* c, dqmc_ut* u, int l);
+
+// iterate(it) :198-293
+static cudaError_t cgi_first(dqmc_ctx* c, dqmc_ut* u)
+{
+    CE(ut_build_stack(c, u));
+    u->last_k = u->last_l = -1;
+    if (u->it_start == 0 || u->it_start == 1) {
+        if (c->current_slice == 1) CE(copy_mats(c, c->Tl, c->greens));
+        else { CE(calculate_greens_full1(c, u, 0, 0)); std::swap(c->Tl, u->greens); }
+        CE(copy_mats(c, c->tmp1, c->Tl));
+        CE(scale_add(c, c->Tr, c->Tl, no_scale(), no_scale(), nullptr, -1.0));    // Tr = G00 - I
+        CE(udt(c, c->Tl, no_scale(), c->Ul, c->Dl, c->Tl, true));
+        CE(copy_mats(c, u->U, c->Ul)); CE(copy_vecs(c, u->D, c->Dl)); CE(copy_mats(c, u->T, c->Tl));
+        CE(udt(c, c->Tr, no_scale(), c->Ur, c->Dr, c->Tr, true));
+        if (u->it_start == 0) {
+            CE(measured_into(c, u->greens, c->tmp1, c->tmp2));
+            u->out_G0l = u->out_Gl0 = u->out_Gll = u->greens;
+            u->it_next = 1;
+            return cudaSuccess;
+        }
+        CE(cgi_advance(c, u, 1));
+        u->it_next = 2;
+        return cudaSuccess;
+    }
+    CE(cgi_recalculate(c, u, u->it_start));
+    u->it_next = u->it_start + 1;
+    return cudaSuccess;
+}
+
+// iterate(it, l) :295-435 (l <= stop)
+static cudaError_t cgi_advance(dqmc_ctx* c, dqmc_ut* u, int l)
+{
+    u->last_k = u->last_l = -1;
+    const int shift = (u->it_start != 1) ? u->it_start : 0;
+    if ((l - shift) % u->it_recalc == 0) return cgi_recalculate(c, u, l);
+    // both remaining branches start with B_l Ul, Tr B_l^-1, B_l U, T B_l^-1
+    CE(slice_left(c, u->s1, c->Ul, l)); std::swap(c->Ul, u->s1);
+    CE(slice_inv_right(c, u->s1, c->Tr, l)); std::swap(c->Tr, u->s1);
+    CE(slice_left(c, u->s1, u->U, l)); std::swap(u->U, u->s1);
+    CE(slice_inv_right(c, u->s1, u->T, l)); std::swap(u->T, u->s1);
+    if (((l - shift) % u->it_recalc) % u->it_safe_mult == 0) {
+        // stabilisation :343-390
+        // Gl0
+        CE(mul(c, c->tmp2, c->Ul, false, c->Tl, false, no_scale(), vec_scale(c, c->Dl)));
+        CE(copy_vecs(c, u->dv, c->Dl));
+        CE(udt(c, c->Ul, vec_scale(c, u->dv), u->s1, c->Dl, c->tmp1, true)); std::swap(c->Ul, u->s1);
+        CE(mul(c, u->s1, c->tmp1, false, c->Tl, false)); std::swap(c->Tl, u->s1);
+        CE(measured_into(c, c->tmp1, c->tmp2, c->curr_U));
+        // G0l
+        CE(mul(c, u->greens, c->Ur, false, c->Tr, false, no_scale(), vec_scale(c, c->Dr)));
+        CE(scale_add(c, u->s1, c->Tr, vec_scale(c, c->Dr), no_scale(), nullptr, 0.0));
+        CE(udt(c, u->s1, no_scale(), c->tmp2, c->Dr, c->Tr, true));
+        CE(mul(c, u->s1, c->Ur, false, c->tmp2, false)); std::swap(c->Ur, u->s1);
+        CE(measured_into(c, c->tmp2, u->greens, c->curr_U));
+        // Gll
+        CE(mul(c, u->greens, u->U, false, u->T, false, no_scale(), vec_scale(c, u->D)));
+        CE(copy_vecs(c, u->dv, u->D));
+        CE(udt(c, u->U, vec_scale(c, u->dv), c->curr_U, u->D, u->tmp, true));
+        CE(mul(c, u->s2, u->tmp, false, u->T, false, vec_scale(c, u->D)));        // D (T' T)
+        CE(udt(c, u->s2, no_scale(), u->tmp, u->D, u->T, true));
+        CE(mul(c, u->U, c->curr_U, false, u->tmp, false));
+        CE(measured_into(c, u->greens, u->greens, c->curr_U));
+    } else {
+        // quick advance :392-420
+        CE(mul(c, c->tmp2, c->Ul, false, c->Tl, false, no_scale(), vec_scale(c, c->Dl)));
+        CE(measured_into(c, c->tmp1, c->tmp2, c->curr_U));
+        CE(mul(c, u->greens, c->Ur, false, c->Tr, false, no_scale(), vec_scale(c, c->Dr)));
+        CE(measured_into(c, c->tmp2, u->greens, c->curr_U));
+        CE(mul(c, u->greens, u->U, false, u->T, false, no_scale(), vec_scale(c, u->D)));
+        CE(measured_into(c, u->greens, u->greens, c->curr_U));
+    }
+    cgi_outputs(c, u);
+    return cudaSuccess;
+}
+
+// =============================================================================================
+// host-facing helpers used by measure.cu
+// =============================================================================================
+cudaError_t ut_iter_begin(dqmc_ctx* c, int recalculate, int start, int stop, int safe_mult)
+{
+    dqmc_ut* u = nullptr;
+    CE(ut_get(c, &u));
+    u->it_recalc = recalculate; u->it_start = start; u->it_stop = stop; u->it_safe_mult = safe_mult;
+    u->it_active = true; u->it_next = -1;
+    return cudaSuccess;
+}
+// advances the iterator; *l = index of the produced triple, or -1 when the iteration is over
+cudaError_t ut_iter_next(dqmc_ctx* c, int* l, const double** G0l, const double** Gl0, const double** Gll)
+{
+    dqmc_ut* u = c->ut;
+    *l = -1;
+    if (!u || !u->it_active) return cudaErrorInvalidValue;
+    if (u->it_next < 0) {
+        if (u->it_start > u->it_stop) { u->it_active = false; return cudaSuccess; }
+        CE(cgi_first(c, u));
+        *l = u->it_next - 1;
+    } else {
+        if (u->it_next > u->it_stop) { u->it_active = false; return cudaSuccess; }
+        CE(cgi_advance(c, u, u->it_next));
+        *l = u->it_next;
+        u->it_next += 1;
+    }
+    *G0l = u->out_G0l; *Gl0 = u->out_Gl0; *Gll = u->out_Gll;
+    return cudaSuccess;
+}
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int32_t dqmc_ut_build_stack(dqmc_ctx* c)
+{
+    ENTER(c);
+    dqmc_ut* u = nullptr;
+    CK(c, ut_get(c, &u));
+    CK(c, ut_build_stack(c, u));
+    CK(c, cudaStreamSynchronize(c->st));
+    return DQMC_OK;
+}
+
+int32_t dqmc_ut_lazy_build(dqmc_ctx* c, int32_t forward_upto, int32_t backward_downto)
+{
+    ENTER(c);
+    if (forward_upto > c->C + 1 || backward_downto > c->C + 1) FAIL(c, DQMC_ERR_INVALID, "dqmc_ut_lazy_build: index out of range");
+    dqmc_ut* u = nullptr;
+    CK(c, ut_get(c, &u));
+    if (forward_upto > 0) CK(c, ut_lazy_build_forward(c, u, forward_upto));
+    if (backward_downto > 0) CK(c, ut_lazy_build_backward(c, u, backward_downto));
+    CK(c, cudaStreamSynchronize(c->st));
+    return DQMC_OK;
+}
+
+int32_t dqmc_ut_greens(dqmc_ctx* c, int32_t k, int32_t l, int32_t measured, double* G)
+{
+    ENTER(c);
+    if (!G || k < 0 || k > c->M || l < 0 || l > c->M) FAIL(c, DQMC_ERR_INVALID, "dqmc_ut_greens: need 0 <= k, l <= n_slices");
+    dqmc_ut* u = nullptr;
+    CK(c, ut_get(c, &u));
+    u->it_active = false;                      // like the reference: breaks a running iteration
+    CK(c, ut_calculate_greens(c, u, k, l));
+    const double* src = u->greens;
+    if (measured) { CK(c, measured_into(c, c->greens_temp, u->greens, c->tmp1)); src = c->greens_temp; }
+    CK(c, d2h_mats(c, G, src, c->nmat));
+    CK(c, cudaStreamSynchronize(c->st));
+    return DQMC_OK;
+}
+
+int32_t dqmc_ut_get_stack_array(dqmc_ctx* c, int32_t chain, int32_t which, int32_t slot, double* out)
+{
+    ENTER(c);
+    if (!out || chain < 0 || chain >= c->B || which < 0 || which > 8) FAIL(c, DQMC_ERR_INVALID, "dqmc_ut_get_stack_array: bad arguments");
+    const int nslots = (which >= 6) ? c->C : c->C + 1;
+    if (slot < 1 || slot > nslots) FAIL(c, DQMC_ERR_INVALID, "dqmc_ut_get_stack_array: slot out of range");
+    dqmc_ut* u = nullptr;
+    CK(c, ut_get(c, &u));
+    double* bases[9] = {u->fu, u->fd, u->ft, u->bu, u->bd, u->bt, u->iu, u->id, u->it};
+    if (which % 3 == 1) {
+        const double* src = uvec(c, bases[which], slot - 1) + (long long)chain * c->nb * c->N;
+        CK(c, cudaMemcpyAsync(out, src, (size_t)c->nb * c->N * 8, cudaMemcpyDeviceToHost, c->st));
+    } else {
+        CK(c, d2h_mats(c, out, umat(c, bases[which], slot - 1) + (long long)chain * c->nb * c->ms, c->nb));
+    }
+    CK(c, cudaStreamSynchronize(c->st));
+    return DQMC_OK;
+}
+
+int32_t dqmc_cgi_begin(dqmc_ctx* c, int32_t recalculate, int32_t start, int32_t stop, int32_t safe_mult)
+{
+    ENTER(c);
+    if (recalculate < 1 || safe_mult < 1 || start < 0 || stop > c->M)
+        FAIL(c, DQMC_ERR_INVALID, "dqmc_cgi_begin: need recalculate, safe_mult >= 1 and 0 <= start, stop <= n_slices");
+    CK(c, ut_iter_begin(c, recalculate, start, stop, safe_mult));
+    return DQMC_OK;
+}
+
+int32_t dqmc_cgi_next(dqmc_ctx* c, int32_t* l, double* G0l, double* Gl0, double* Gll)
+{
+    ENTER(c);
+    if (!l) FAIL(c, DQMC_ERR_INVALID, "dqmc_cgi_next: null argument");
+    if (!c->ut || !c->ut->it_active) FAIL(c, DQMC_ERR_INVALID, "dqmc_cgi_next: no iteration in progress (call dqmc_cgi_begin)");
+    int li = -1; const double *a = nullptr, *b = nullptr, *d = nullptr;
+    CK(c, ut_iter_next(c, &li, &a, &b, &d));
+    *l = li;
+    if (li >= 0) {
+        if (G0l) CK(c, d2h_mats(c, G0l, a, c->nmat));
+        if (Gl0) CK(c, d2h_mats(c, Gl0, b, c->nmat));
+        if (Gll) CK(c, d2h_mats(c, Gll, d, c->nmat));
+    }
+    CK(c, cudaStreamSynchronize(c->st));
+    return DQMC_OK;
+}
+
+}  // extern "C"

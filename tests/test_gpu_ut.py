@@ -1,0 +1,212 @@
+"""GPU parity of the unequal-time path (montecarlo.jl_b200/csrc/ut.cu, through the C ABI) against the CPU
+oracle (oracle/dqmc_ref_ut.inc.c), the reference's own tests for it (test/DQMC/unequal_time_stack.jl) and
+size-independent properties.  Run with `-m gpu` on a B200.
+
+Tolerance: 1e-10 relative to max|G| for every Green's function (north_star); the reference's own bounds
+(2e-14 / 1e-10 absolute, unequal_time_stack.jl:116-172) are asserted where it states them.
+"""
+import numpy as np
+import pytest
+
+from oracle import model as OM
+
+from test_gpu_parity import GTOL, make_pair, relerr
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # kind, Ls, U, beta, safe_mult
+    ("chain", (6,), 1.0, 5.0, 5),           # HubbardModel(6, 1) of the reference test (shorter beta)
+    ("chain", (6,), -1.0, 5.0, 5),          # two flavor blocks
+    ("square", (4, 4), 4.0, 2.0, 10),       # cfg-1 model
+    ("square", (6, 6), -4.0, 3.0, 8),       # repulsive, M = 30 with ragged ranges (8, 7, 8, 7)
+    ("honeycomb", (3, 3), 4.0, 2.0, 10),    # two-site basis (cfg 5's lattice)
+]
+
+
+def udt_product(ctx_or_chain, getter, prefix, slot):
+    U = getter(prefix + "_u", slot)
+    D = getter(prefix + "_d", slot)
+    T = getter(prefix + "_t", slot)
+    return np.stack([U[:, :, b] @ np.diag(D[:, b]) @ T[:, :, b] for b in range(U.shape[2])], axis=2)
+
+
+@pytest.mark.parametrize("kind,Ls,U,beta,sm", CASES)
+def test_ut_build_stack_matches_oracle(b200, kind, Ls, U, beta, sm):
+    """forward / backward / inverse stacks: U D T of every slot equals the oracle's (the factors themselves
+    are not unique on exact norm ties, the product is) -- unequal_time_stack.jl:71-91, 189-247."""
+    ctx, chains = make_pair(b200, kind, Ls, U=U, beta=beta, B=2, safe_mult=sm)
+    ctx.ut_build_stack()
+    for b, c in enumerate(chains):
+        c.ut_build_stack()
+        for prefix, slots in (("forward", range(0, c.C + 1)), ("backward", range(0, c.C + 1)), ("inv", range(0, c.C))):
+            for s in slots:
+                got = udt_product(ctx, lambda w, sl: ctx.ut_stack_array(w, sl + 1, chain=b), prefix, s)
+                want = udt_product(c, c.ut_array, prefix, s)
+                assert relerr(got, want) < 1e-11, (prefix, s)
+                u = ctx.ut_stack_array(prefix + "_u", s + 1, chain=b)
+                for blk in range(c.nb):
+                    assert np.abs(u[:, :, blk].T @ u[:, :, blk] - np.eye(c.N)).max() < 1e-12
+
+
+def test_ut_stack_equals_equal_time_stack(b200):
+    """unequal_time_stack.jl:71-91 on the device: forward ut stack == u/d/t_stack after build_stack."""
+    ctx, chains = make_pair(b200, "chain", (6,), U=1.0, beta=15.0, B=1, safe_mult=5)
+    ctx.forward_build_stack()
+    ctx.ut_build_stack()
+    C = chains[0].C
+    for s in range(1, C + 2):
+        for w, uw in (("u_stack", "forward_u"), ("d_stack", "forward_d"), ("t_stack", "forward_t")):
+            assert np.allclose(ctx.stack_array(w, s), ctx.ut_stack_array(uw, s), rtol=1e-12, atol=1e-14)
+    # lazy builds only touch the requested slots (unequal_time_stack.jl:24-69)
+    ctx2, _ = make_pair(b200, "chain", (6,), U=1.0, beta=15.0, B=1, safe_mult=5)
+    ctx2.ut_lazy_build(forward_upto=4)
+    for s in range(1, 5):
+        assert np.allclose(ctx.ut_stack_array("forward_u", s), ctx2.ut_stack_array("forward_u", s), rtol=1e-12, atol=1e-14)
+    for s in range(5, C + 2):
+        assert np.all(ctx2.ut_stack_array("forward_u", s) == 0)
+    ctx2.ut_lazy_build(backward_downto=C - 1)
+    for s in range(C - 1, C + 2):
+        assert np.allclose(ctx.ut_stack_array("backward_u", s), ctx2.ut_stack_array("backward_u", s), rtol=1e-12, atol=1e-14)
+    assert np.all(ctx2.ut_stack_array("backward_u", C - 2) == 0)
+
+
+@pytest.mark.parametrize("kind,Ls,U,beta,sm", CASES)
+def test_ut_greens_matches_oracle(b200, kind, Ls, U, beta, sm):
+    """greens(mc, k, l) and calculate_greens(mc, k, l) for k >= l (full1) and k < l (full2), incl. the
+    range-boundary cases of compute_*_udt_block! (unequal_time_stack.jl:400-533)."""
+    ctx, chains = make_pair(b200, kind, Ls, U=U, beta=beta, B=2, safe_mult=sm)
+    M = chains[0].M
+    r1 = chains[0].ranges[0][1]
+    pairs = [(0, 0), (M, M), (M, 0), (0, M), (r1, 0), (r1 + 1, r1), (r1, r1 + 1), (M - 1, 2), (3, M - 2),
+             (M // 2, M // 2), (M // 2 + 3, M // 2 - 4), (1, 0), (0, 1), (M, M - 1)]
+    for (k, l) in pairs:
+        G = ctx.ut_greens(k, l, measured=True)
+        Ge = ctx.ut_greens(k, l, measured=False)
+        for b, c in enumerate(chains):
+            assert relerr(Ge[:, :, :, b], c.ut_calculate_greens(k, l)) < GTOL, (k, l)
+            assert relerr(G[:, :, :, b], c.ut_greens(k, l)) < GTOL, (k, l)
+
+
+def test_ut_equal_time_consistency(b200):
+    """unequal_time_stack.jl:97-113: G(k, k) from the ut stack == calculate_greens(mc, k); G(t, 0) == -G(t, M)."""
+    ctx, chains = make_pair(b200, "chain", (6,), U=1.0, beta=15.0, B=2, safe_mult=5)
+    M = chains[0].M
+    for k in list(range(0, M + 1, 7)) + [M]:
+        G1 = ctx.calculate_greens_at(k, 5)
+        G2 = ctx.ut_greens(k, k, measured=False)
+        assert np.abs(G1 - G2).max() < 1e-12
+    for t in range(0, M, 11):
+        G1 = ctx.ut_greens(t, 0)
+        G2 = ctx.ut_greens(t, M)
+        assert np.allclose(G1, -G2, atol=1e-12, rtol=1e-9)
+
+
+def test_ut_U0_analytic(b200):
+    """test/ED/ED_tests.jl:284-299: U = 0 => G(k, l) = e^{-(k-l) dtau T} (1 + e^{-beta T})^-1 (k >= l)."""
+    ctx, chains = make_pair(b200, "square", (4, 4), U=0.0, beta=2.0, B=1, safe_mult=5)
+    c = chains[0]
+    w, V = np.linalg.eigh(OM.hopping_matrix("square", (4, 4)))
+    f = 1.0 / (1.0 + np.exp(-c.beta * w))
+    for (k, l) in [(0, 0), (7, 0), (c.M, 0), (13, 4), (9, 9)]:
+        want = (V * (np.exp(-(k - l) * c.delta_tau * w) * f)) @ V.T
+        assert np.abs(ctx.ut_greens(k, l)[:, :, 0, 0] - want).max() < 1e-12
+    for (k, l) in [(0, 5), (3, 17), (0, c.M)]:
+        want = -(V * (np.exp(-(k - l) * c.delta_tau * w) * (1.0 - f))) @ V.T
+        assert np.abs(ctx.ut_greens(k, l)[:, :, 0, 0] - want).max() < 1e-12
+
+
+@pytest.mark.parametrize("kind,Ls,U,beta,sm", CASES)
+@pytest.mark.parametrize("recalc_mult", [1, 2])
+def test_combined_greens_iterator_matches_oracle(b200, kind, Ls, U, beta, sm, recalc_mult):
+    """CombinedGreensIterator: every (G0l, Gl0, Gll) equals the oracle's iterator output (same recalculate /
+    stabilise / quick-advance schedule, greens_iterators.jl:295-435)."""
+    ctx, chains = make_pair(b200, kind, Ls, U=U, beta=beta, B=2, safe_mult=sm)
+    ctx.build_stack()
+    for c in chains:
+        c.init()
+    # With recalculate > safe_mult the quick-advance steps amplify rounding differences: the reference
+    # algorithm itself is then only good to ~1e-8 on Gll at |U| = 4 (its own test allows 1e-10 absolute at
+    # U = 1, unequal_time_stack.jl:164-171).  The device has to be as close to the oracle as the oracle is to
+    # the from-scratch G(k, l): tol = 1e-10 + (oracle's own error at that l).
+    exact = None
+    if recalc_mult > 1:
+        exact = [[(c.ut_greens(0, k), c.ut_greens(k, 0), c.ut_greens(k, k)) for k in range(c.M + 1)] for c in chains]
+        for c in chains:
+            c.init()
+    its = [c.combined_greens_iterator(recalculate=recalc_mult * sm) for c in chains]
+    n = 0
+    for (l, g0l, gl0, gll) in ctx.combined_greens_iterator(sm, recalculate=recalc_mult * sm):
+        for b, it in enumerate(its):
+            (lo, o0l, ol0, oll) = next(it)
+            assert lo == l
+            for name, got, want, i in (("G0l", g0l, o0l, 0), ("Gl0", gl0, ol0, 1), ("Gll", gll, oll, 2)):
+                tol = GTOL + (relerr(want, exact[b][l][i]) if exact else 0.0)
+                assert relerr(got[:, :, :, b], want) < tol, (name, l, tol)
+        n += 1
+    assert n == chains[0].M + 1
+    # the iteration leaves the sweep machinery intact: G, conf and the next sweep still match the oracle
+    acc = ctx.sweep(1)
+    G = ctx.greens()
+    for b, c in enumerate(chains):
+        a = c.local_sweep()
+        assert a == acc[b]
+        assert relerr(G[:, :, :, b], c.greens) < GTOL
+
+
+def test_combined_greens_iterator_reference_bounds(b200):
+    """unequal_time_stack.jl:116-172 on the device: iterator vs greens(k, 0) / greens(0, k) / G(k, k):
+    < 2e-14 with recalculate = safe_mult (we allow 1e-13: different but equivalent pivot tie-breaks and
+    fused scalings), < 1e-10 with recalculate = 4 safe_mult."""
+    ctx, chains = make_pair(b200, "chain", (6,), U=1.0, beta=15.0, B=1, safe_mult=5)
+    M = chains[0].M
+    ctx.build_stack()
+    Gk0 = [ctx.ut_greens(k, 0) for k in range(M + 1)]
+    G0k = [ctx.ut_greens(0, k) for k in range(M + 1)]
+    Gkk = [ctx.ut_greens(k, k) for k in range(M + 1)]
+    ctx.build_stack()
+    for recalc, tol in ((5, 1e-13), (20, 1e-10)):
+        for (l, g0l, gl0, gll) in ctx.combined_greens_iterator(5, recalculate=recalc, start=0, stop=M):
+            assert np.abs(gl0 - Gk0[l]).max() < tol
+            assert np.abs(g0l - G0k[l]).max() < tol
+            assert np.abs(gll - Gkk[l]).max() < tol
+
+
+@pytest.mark.parametrize("start", [1, 7])
+def test_combined_greens_iterator_start_variants(b200, start):
+    ctx, chains = make_pair(b200, "chain", (6,), U=-1.0, beta=4.0, B=2, safe_mult=5)
+    ctx.build_stack()
+    for c in chains:
+        c.init()
+    M = chains[0].M
+    its = [c.combined_greens_iterator(recalculate=10, start=start, stop=M - 3) for c in chains]
+    ls = []
+    for (l, g0l, gl0, gll) in ctx.combined_greens_iterator(5, recalculate=10, start=start, stop=M - 3):
+        for b, it in enumerate(its):
+            (lo, o0l, ol0, oll) = next(it)
+            assert lo == l
+            assert relerr(g0l[:, :, :, b], o0l) < GTOL and relerr(gl0[:, :, :, b], ol0) < GTOL
+            assert relerr(gll[:, :, :, b], oll) < GTOL
+        ls.append(l)
+    assert ls == list(range(start, M - 2))
+
+
+def test_ut_cfg5_shape(b200):
+    """Largest configuration (honeycomb L = 12, N = 288, the register-QR limit), checked through
+    size-independent properties of the definition: G(beta, beta) = G(0, 0), G(beta, 0) = 1 - G(0, 0) and
+    G(0, beta) = -G(0, 0)."""
+    ctx, chains = make_pair(b200, "honeycomb", (12, 12), U=4.0, beta=1.0, B=2, safe_mult=5)
+    ctx.build_stack()
+    G00 = ctx.measured_greens()
+    last = None
+    for (l, g0l, gl0, gll) in ctx.combined_greens_iterator(5, fetch=True):
+        last = (l, g0l, gl0, gll)
+        if l == 0:
+            assert relerr(gll, G00) < 1e-12
+    l, g0l, gl0, gll = last
+    N = chains[0].N
+    eye = np.eye(N)[:, :, None, None]
+    assert l == chains[0].M
+    assert relerr(gll, G00) < 1e-9              # G(beta, beta) = G(0, 0)
+    assert np.abs(gl0 - (eye - G00)).max() < 1e-9
+    assert np.abs(g0l + G00).max() < 1e-9
