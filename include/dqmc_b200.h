@@ -152,6 +152,43 @@ int32_t dqmc_reduce_observables(dqmc_ctx* ctx, void* nccl_comm);
 /* copy out: count, then mean and variance-of-the-mean inputs (sum, sumsq), N x N x n_flavors each. */
 int32_t dqmc_get_observables(dqmc_ctx* ctx, double* count, double* sum, double* sumsq);
 
+/* ---- device-side Wick kernels (src/flavors/DQMC/measurements) ---------------------------------------- */
+/* Lattice tables the kernels need: Bravais srctrg2dir (lattices/lattice_cache.jl:69-78, 224-240; n_bravais x
+ * n_bravais, column-major [src, trg], 1-based directions), the hopping matrix mc.stack.hopping_matrix (N x N)
+ * for the kinetic energy and the model's U (HubbardModel.jl:160-183).  Site = cell + n_bravais * basis. */
+int32_t dqmc_set_lattice(dqmc_ctx* ctx, int32_t n_bravais, int32_t n_basis, const int32_t* srctrg2dir,
+                         const double* hopping_matrix, double U);
+/* Observables, in this order inside a result vector (offsets[k] .. offsets[k+1], offsets[DQMC_OBS_COUNT] = length):
+ * occupation (N x n_flavors, occupation.jl:44-70), kinetic / interaction / total energy (energy.jl:119-165),
+ * equal-time charge and spin x/y/z density correlations (n_bravais x n_basis x n_basis each, EachSitePairByDistance,
+ * full_cdc_kernel / full_sdc_*_kernel), and their time-integrated susceptibilities (TimeIntegral). */
+#define DQMC_OBS_OCC 0
+#define DQMC_OBS_KINETIC 1
+#define DQMC_OBS_INTERACTION 2
+#define DQMC_OBS_TOTAL_ENERGY 3
+#define DQMC_OBS_CDC 4
+#define DQMC_OBS_SDC_X 5
+#define DQMC_OBS_SDC_Y 6
+#define DQMC_OBS_SDC_Z 7
+#define DQMC_OBS_CDS 8
+#define DQMC_OBS_SDS_X 9
+#define DQMC_OBS_SDS_Y 10
+#define DQMC_OBS_SDS_Z 11
+#define DQMC_OBS_COUNT 12
+int32_t dqmc_measurement_layout(dqmc_ctx* ctx, int32_t* offsets /* [DQMC_OBS_COUNT + 1] */);
+/* apply!(::Greens, ...) (measurements/generic.jl:287-310) for every chain: observables 0..7 from greens!(mc);
+ * the stack must be at (slice 1, direction +1) like the reference's measurement point (DQMC.jl:217). */
+int32_t dqmc_measure_equal_time(dqmc_ctx* ctx);
+/* apply!(::TimeIntegral, ...) (generic.jl:337-372): runs the CombinedGreensIterator on the device and sums
+ * weight_l * kernel(G00, G0l, Gl0, Gll) into observables 8..11 (weight = dtau, halved at l = 0 and l = M). */
+int32_t dqmc_measure_time_integral(dqmc_ctx* ctx, int32_t recalculate, int32_t safe_mult, double delta_tau);
+/* values of the last measurement, [nchains][length] (what each chain's LogBinner would be pushed). */
+int32_t dqmc_get_measurements(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, double* out);
+/* device accumulator block [count_equal_time, count_time_integral | sum[length] | sumsq[length]] over chains and
+ * calls; dqmc_reduce_observables all-reduces it together with the Green's function block. */
+int32_t dqmc_measurement_buffer(dqmc_ctx* ctx, void** device_ptr, int64_t* n_doubles);
+int32_t dqmc_get_measurement_stats(dqmc_ctx* ctx, double* counts /* [2] */, double* sum, double* sumsq);
+
 /* ---- operator level: the reference's linalg "operator API", batched over host arrays ------- */
 /* vmul!(C, op(A), op(B)) (linalg/real.jl:7-15, 72-102) */
 int32_t dqmc_op_vmul(int32_t device, int32_t n, int32_t batch, int32_t transA, int32_t transB,

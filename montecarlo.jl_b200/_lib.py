@@ -82,6 +82,13 @@ def load():
         "dqmc_ut_get_stack_array": (i32, [vp, i32, i32, i32, dp]),
         "dqmc_cgi_begin": (i32, [vp, i32, i32, i32, i32]),
         "dqmc_cgi_next": (i32, [vp, i32p, dp, dp, dp]),
+        "dqmc_set_lattice": (i32, [vp, i32, i32, i32p, dp, C.c_double]),
+        "dqmc_measurement_layout": (i32, [vp, i32p]),
+        "dqmc_measure_equal_time": (i32, [vp]),
+        "dqmc_measure_time_integral": (i32, [vp, i32, i32, C.c_double]),
+        "dqmc_get_measurements": (i32, [vp, i32, i32, dp]),
+        "dqmc_measurement_buffer": (i32, [vp, C.POINTER(vp), i64p]),
+        "dqmc_get_measurement_stats": (i32, [vp, dp, dp, dp]),
         "dqmc_accumulate_greens": (i32, [vp]),
         "dqmc_observable_buffer": (i32, [vp, C.POINTER(vp), i64p]),
         "dqmc_reduce_observables": (i32, [vp, vp]),

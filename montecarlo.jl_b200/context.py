@@ -247,6 +247,54 @@ class Context:
                 return
             yield (l.value, *bufs)
 
+    # ------------------------------------------------------------------ device-side Wick kernels
+    OBS_NAMES = ("occ", "K", "V", "E", "cdc", "sdxc", "sdyc", "sdzc", "cds", "sdxs", "sdys", "sdzs")
+
+    def set_lattice(self, srctrg2dir, n_basis, hopping_matrix, U):
+        """srctrg2dir: (n_bravais, n_bravais) 0-based Bravais direction of every (src, trg) pair."""
+        s2d = np.asfortranarray(np.array(srctrg2dir, dtype=np.int32) + 1)
+        nbr = s2d.shape[0]
+        T = _f64(hopping_matrix, (self.N, self.N))
+        self._ck(self._L.dqmc_set_lattice(self._h, nbr, int(n_basis), s2d.ctypes.data_as(_lib.i32p), _dp(T), float(U)))
+        self._nbr, self._nbasis = nbr, int(n_basis)
+        off = (C.c_int32 * (len(self.OBS_NAMES) + 1))()
+        self._ck(self._L.dqmc_measurement_layout(self._h, off))
+        self._obs_off = list(off)
+
+    def measure_equal_time(self):
+        self._ck(self._L.dqmc_measure_equal_time(self._h))
+
+    def measure_time_integral(self, safe_mult, delta_tau, recalculate=None):
+        recalculate = 2 * int(safe_mult) if recalculate is None else int(recalculate)
+        self._ck(self._L.dqmc_measure_time_integral(self._h, recalculate, int(safe_mult), float(delta_tau)))
+
+    def _split_obs(self, vec):
+        out = {}
+        for k, name in enumerate(self.OBS_NAMES):
+            v = vec[..., self._obs_off[k]:self._obs_off[k + 1]]
+            if name == "occ":
+                pass
+            elif name in ("K", "V", "E"):
+                v = v[..., 0]
+            else:
+                v = v.reshape(v.shape[:-1] + (self._nbasis, self._nbasis, self._nbr)).swapaxes(-1, -3)
+            out[name] = v
+        return out
+
+    def measurements(self, chain0=0, nchains=None):
+        """-> dict name -> per-chain values of the last measurement; pair observables are (B, n_bravais, basis, basis)."""
+        nchains = self.B - chain0 if nchains is None else nchains
+        out = np.zeros((nchains, self._obs_off[-1]))
+        self._ck(self._L.dqmc_get_measurements(self._h, chain0, nchains, _dp(out)))
+        return self._split_obs(out)
+
+    def measurement_stats(self):
+        """-> (count_equal_time, count_time_integral, dict of sums, dict of sums of squares)."""
+        n = self._obs_off[-1]
+        cnt = np.zeros(2); s = np.zeros(n); s2 = np.zeros(n)
+        self._ck(self._L.dqmc_get_measurement_stats(self._h, _dp(cnt), _dp(s), _dp(s2)))
+        return cnt[0], cnt[1], self._split_obs(s), self._split_obs(s2)
+
     # ------------------------------------------------------------------ observables
     def accumulate_greens(self):
         self._ck(self._L.dqmc_accumulate_greens(self._h))

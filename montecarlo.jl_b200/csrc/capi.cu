@@ -338,6 +338,7 @@ int32_t dqmc_destroy(dqmc_ctx* c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     ut_destroy(c);
+    meas_destroy(c);
     for (void* p : c->allocs) cudaFree(p);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -754,6 +755,11 @@ int32_t dqmc_reduce_observables(dqmc_ctx* c, void* comm)
     // ncclDouble = 8, ncclSum = 0 (nccl.h)
     const int rc = fn(c->obs, c->obs, (size_t)c->obs_len, 8, 0, comm, c->st);
     if (rc != 0) FAIL(c, DQMC_ERR_CUDA, "ncclAllReduce failed");
+    {   // the Wick-kernel accumulators of measure.cu ride along
+        void* mptr = nullptr; int64_t mlen = 0;
+        if (c->meas && dqmc_measurement_buffer(c, &mptr, &mlen) == DQMC_OK && mlen > 0)
+            if (fn(mptr, mptr, (size_t)mlen, 8, 0, comm, c->st) != 0) FAIL(c, DQMC_ERR_CUDA, "ncclAllReduce failed");
+    }
     CK(c, cudaStreamSynchronize(c->st));
     return DQMC_OK;
 }

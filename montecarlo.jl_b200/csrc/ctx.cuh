@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <string>
 #include <utility>
 #include <vector>
@@ -12,7 +13,8 @@
 
 using namespace dqmc;
 
-struct dqmc_ut;   // ut.cu
+struct dqmc_ut;     // ut.cu
+struct dqmc_meas;   // measure.cu
 
 struct dqmc_ctx {
     int N = 0, M = 0, nb = 1, kind = 0, B = 0, C = 0;
@@ -46,6 +48,7 @@ struct dqmc_ctx {
     bool prof_on = false; int prof_depth = 0;
     std::vector<cudaEvent_t> prof_pool; size_t prof_used = 0;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_spans;
+    dqmc_meas* meas = nullptr;         // lattice tables + observable buffers (measure.cu)
     dqmc_ut* ut = nullptr;             // UnequalTimeStack + iterator state, allocated on first use (ut.cu)
 };
 
@@ -116,4 +119,5 @@ cudaError_t copy_mats(dqmc_ctx* c, double* dst, const double* src);
 cudaError_t copy_vecs(dqmc_ctx* c, double* dst, const double* src);
 cudaError_t ident(dqmc_ctx* c, double* A);
 cudaError_t ones(dqmc_ctx* c, double* v);
-void ut_destroy(dqmc_ctx* c);   // ut.cu
+void ut_destroy(dqmc_ctx* c);     // ut.cu
+void meas_destroy(dqmc_ctx* c);   // measure.cu

@@ -1,0 +1,94 @@
+"""GPU parity of the device-side Wick kernels (montecarlo.jl_b200/csrc/measure.cu, through the C ABI) against
+oracle/measure.py evaluated on the CPU oracle's Green's functions.  Run with `-m gpu` on a B200.
+
+Tolerance: 1e-9 relative to the largest entry of each observable (sums of ~N^2 products of Green's function
+entries that themselves agree to 1e-10).
+"""
+import numpy as np
+import pytest
+
+from oracle import measure as OMS
+from oracle import model as OM
+
+from test_gpu_parity import make_pair
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # kind, Ls, n_basis, U, beta, safe_mult
+    ("square", (4, 4), 1, 4.0, 2.0, 10),        # attractive: one flavor block (DiagonallyRepeatingMatrix kernels)
+    ("square", (4, 4), 1, -4.0, 2.0, 5),        # repulsive: two flavor blocks (BlockDiagonal kernels)
+    ("honeycomb", (3, 3), 2, 4.0, 1.0, 5),      # two-site basis: temp[dir, b1, b2]
+    ("honeycomb", (2, 3), 2, -4.0, 1.0, 5),
+]
+
+
+def close(got, want, tol=1e-9):
+    return np.abs(np.asarray(got) - np.asarray(want)).max() <= tol * max(np.abs(want).max(), 1.0)
+
+
+@pytest.mark.parametrize("kind,Ls,nbasis,U,beta,sm", CASES)
+def test_equal_time_observables(b200, kind, Ls, nbasis, U, beta, sm):
+    ctx, chains = make_pair(b200, kind, Ls, U=U, beta=beta, B=3, safe_mult=sm)
+    T = OM.hopping_matrix(kind, Ls)
+    s2d = OMS.bravais_srctrg2dir(Ls)
+    ctx.set_lattice(s2d, nbasis, T, U)
+    ctx.build_stack()
+    ctx.sweep(1)
+    ctx.measure_equal_time()
+    got = ctx.measurements()
+    for b, c in enumerate(chains):
+        c.init(); c.local_sweep()
+        want = OMS.equal_time(c.measured_greens(), T, U, s2d, nbasis)
+        for name in ("occ", "K", "V", "E", "cdc", "sdxc", "sdyc", "sdzc"):
+            assert close(got[name][b], want[name]), (name, b)
+    # accumulators: count, sum and sum of squares over chains; a second call doubles them
+    ctx.measure_equal_time()
+    n_et, n_ti, s, s2 = ctx.measurement_stats()
+    assert n_et == 2 * ctx.B and n_ti == 0
+    assert close(s["cdc"], 2 * got["cdc"].sum(axis=0))
+    assert close(s2["K"], 2 * (got["K"] ** 2).sum())
+
+
+@pytest.mark.parametrize("kind,Ls,nbasis,U,beta,sm", CASES)
+def test_time_integrated_observables(b200, kind, Ls, nbasis, U, beta, sm):
+    ctx, chains = make_pair(b200, kind, Ls, U=U, beta=beta, B=2, safe_mult=sm)
+    T = OM.hopping_matrix(kind, Ls)
+    s2d = OMS.bravais_srctrg2dir(Ls)
+    ctx.set_lattice(s2d, nbasis, T, U)
+    ctx.build_stack()
+    ctx.measure_time_integral(sm, 0.1, recalculate=sm)
+    got = ctx.measurements()
+    for b, c in enumerate(chains):
+        c.init()
+        G00 = c.measured_greens()
+        want = OMS.time_integral(G00, c.combined_greens_iterator(recalculate=sm), c.delta_tau, c.M, s2d, nbasis)
+        for name in ("cds", "sdxs", "sdys", "sdzs"):
+            assert close(got[name][b], want[name]), (name, b)
+    n_et, n_ti, s, s2 = ctx.measurement_stats()
+    assert n_et == 0 and n_ti == ctx.B
+    # the sweep after a measurement is unaffected
+    acc = ctx.sweep(1)
+    for b, c in enumerate(chains):
+        assert c.local_sweep() == acc[b]
+
+
+def test_U0_susceptibility_is_exact(b200):
+    """U = 0: chi_c(q = 0) = sum_dir cds[dir] = integral of <N(tau) N(0)> / N_sites = beta <N>^2 / N_sites for a
+    conserved total charge N (all chains identical, no Monte Carlo noise)."""
+    kind, Ls = "square", (4, 4)
+    ctx, chains = make_pair(b200, kind, Ls, U=0.0, beta=2.0, B=2, safe_mult=5, mu=0.3)
+    T = OM.hopping_matrix(kind, Ls, mu=0.3)
+    ctx.set_lattice(OMS.bravais_srctrg2dir(Ls), 1, T, 0.0)
+    ctx.build_stack()
+    ctx.measure_equal_time()
+    ctx.measure_time_integral(5, 0.1, recalculate=5)
+    got = ctx.measurements()
+    w, _ = np.linalg.eigh(T)
+    f = 1.0 / (1.0 + np.exp(2.0 * w))
+    Ntot = 2.0 * f.sum()
+    varN = 2.0 * (f * (1.0 - f)).sum()
+    # <N(tau) N(0)> = <N^2> for conserved N: the trapezoid rule integrates a constant exactly
+    assert abs(got["cds"][0].sum() - 2.0 * (Ntot ** 2 + varN) / 16) < 1e-9
+    assert abs(got["cdc"][0].sum() - (Ntot ** 2 + varN) / 16) < 1e-10
+    assert abs(got["occ"][0].sum() * 2 - Ntot) < 1e-11
