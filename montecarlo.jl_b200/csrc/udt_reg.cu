@@ -54,7 +54,7 @@ static bool udt_level_geometry(int n, UdtLevel& g)
 {
     const int rpl = (n + 31) / 32;
     if (rpl > 9) return false;
-    const int maxw = (rpl <= 4) ? 16 : ((rpl <= 6) ? 9 : 8);   // matches the __launch_bounds__ below
+    const int maxw = (rpl <= 4) ? 16 : ((rpl <= 6) ? 12 : 8);  // matches the __launch_bounds__ below
     static const int min_cs = getenv("DQMC_UDT_CS") ? atoi(getenv("DQMC_UDT_CS")) : 1;   // experiment knob
     for (int cs = min_cs; cs <= 8; cs *= 2) {
         const int nloc = (n + cs - 1) / cs;
@@ -212,7 +212,7 @@ __device__ __forceinline__ double fast_rcp(double x)
 // QR steps [0, jstop) of one level
 // ================================================================================================
 template <int RPL>
-__global__ void __launch_bounds__((RPL <= 4) ? 512 : ((RPL <= 6) ? 288 : 256))
+__global__ void __launch_bounds__((RPL <= 4) ? 512 : ((RPL <= 6) ? 384 : 256))
 udt_steps_kernel(const UdtParams p, const UdtLevel L)
 {
     cg::cluster_group cluster = cg::this_cluster();
@@ -578,16 +578,33 @@ static cudaError_t launch_formq(const UdtParams& p, cudaStream_t st)
 
 bool udt_reg_supported(int n) { UdtLevel g{}; return udt_level_geometry(n, g); }
 
-// scratch needed per matrix besides Vwork: Tphys (ld * n doubles), the trailing-block buffers
-// ((n/2)^2 + (n/4)^2 + ... < n^2 / 2 doubles, rounded-up leading dimensions) and two column maps (2 n ints)
-size_t udt_reg_scratch_doubles(int n, int ld) { return (size_t)ld * n + (size_t)(n + 2) * (n + 2) / 2 + 64; }
+// Level sizes are the sizes at which the geometry gets cheaper: <= 256 needs 4 SMs per matrix (37 matrices
+// in flight), <= 192 two (74: 12 warps of 8 columns x 6 register rows), <= 128 one (148).  Returns the size
+// of the trailing block the level that starts with nk columns hands on (0: it finishes the factorisation).
+static int udt_next_level_size(int nk)
+{
+    static const bool one_level = getenv("DQMC_UDT_ONE_LEVEL") != nullptr;   // A/B knob
+    if (one_level || nk <= 64) return 0;
+    static const int sizes[4] = {256, 192, 128, 64};
+    for (int k = 0; k < 4; ++k)
+        if (sizes[k] < nk) return sizes[k];
+    return 0;
+}
+
+// scratch needed per matrix besides Vwork: Tphys (ld * n doubles), one trailing-block buffer per level
+// (rounded-up leading dimensions) and two column maps (2 n ints)
+size_t udt_reg_scratch_doubles(int n, int ld)
+{
+    size_t tot = (size_t)ld * n + 64;
+    for (int nk = udt_next_level_size(n); nk > 0; nk = udt_next_level_size(nk)) tot += (size_t)((nk + 1) & ~1) * nk;
+    return tot;
+}
 size_t udt_reg_scratch_ints(int n) { return (size_t)2 * n + 16; }
 
 cudaError_t launch_udt_reg(const UdtParams& p, cudaStream_t st)
 {
     if (p.batch <= 0) return cudaSuccess;
     if (!p.scratch || !p.iscratch) return cudaErrorInvalidValue;
-    static const bool one_level = getenv("DQMC_UDT_ONE_LEVEL") != nullptr;   // A/B knob
     const int n = p.n;
     // scratch layout: [Tphys: batch x ld*n] [S level 0: batch x ...] [S level 1: batch x ...] ...
     double* Tphys_base = p.scratch;
@@ -603,8 +620,7 @@ cudaError_t launch_udt_reg(const UdtParams& p, cudaStream_t st)
     while (nk > 0) {
         UdtLevel g{};
         if (!udt_level_geometry(nk, g)) return cudaErrorInvalidConfiguration;
-        int jstop = nk;
-        if (!one_level && nk > 64) jstop = nk / 2;
+        const int jstop = nk - udt_next_level_size(nk);
         g.n = nk; g.jstop = jstop; g.joff = joff; g.ld = ldin;
         g.A = Ain; g.strideA = strideIn; g.cmap = cmap_in; g.strideCmap = strideCm;
         g.Tphys = direct_T ? p.T : Tphys_base; g.strideTp = direct_T ? p.strideT : strideTp;
