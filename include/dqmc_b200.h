@@ -108,6 +108,16 @@ int32_t dqmc_sweep_spatial(dqmc_ctx* ctx, const double* uniforms, const uint8_t*
                            double* probs, uint8_t* decisions, int64_t* accepted);
 int32_t dqmc_set_sweep_index(dqmc_ctx* ctx, int64_t sweep);
 
+/* ---- global updates (src/flavors/DQMC/updates/global_updates.jl) ----------------------------------------- */
+/* global_update (:203-219) for every chain: proposed = [n_chains][M][N] configurations (propose_conf! done by the
+ * caller: GlobalShuffle, SpatialShuffle, ...) or NULL for GlobalFlip (:237-248, conf -> -conf).  The weight ratio
+ * is det(G_old) / det(G_new) from the diagonal factors (inv_det :70-137, propose_global_from_conf :147-179);
+ * accepted chains keep the proposal, rejected ones their old configuration; afterwards the stack is rebuilt
+ * (accept_global! :181-198) and sits at (slice 1, direction +1).  uniforms: [n_chains] or NULL (counter RNG with
+ * step = 2M, site = 0, dqmc_rng.h).  accepted / probs: [n_chains], may be NULL; probs = |exp(-dE_boson) detratio|. */
+int32_t dqmc_global_update(dqmc_ctx* ctx, const int8_t* proposed, const double* uniforms, int32_t safe_mult,
+                           int64_t* accepted, double* probs);
+
 /* ---- results ------------------------------------------------------------------------------- */
 /* mc.stack.greens (effective Green's function), N x N x n_flavors per chain. */
 int32_t dqmc_get_greens(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, double* G);

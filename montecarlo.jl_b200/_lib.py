@@ -82,6 +82,7 @@ def load():
         "dqmc_ut_get_stack_array": (i32, [vp, i32, i32, i32, dp]),
         "dqmc_cgi_begin": (i32, [vp, i32, i32, i32, i32]),
         "dqmc_cgi_next": (i32, [vp, i32p, dp, dp, dp]),
+        "dqmc_global_update": (i32, [vp, i8p, dp, i32, i64p, dp]),
         "dqmc_set_lattice": (i32, [vp, i32, i32, i32p, dp, C.c_double]),
         "dqmc_measurement_layout": (i32, [vp, i32p]),
         "dqmc_measure_equal_time": (i32, [vp]),

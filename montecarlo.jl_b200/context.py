@@ -163,6 +163,23 @@ class Context:
                                             acc.ctypes.data_as(_lib.i64p)))
         return acc, probs, dec
 
+    def global_update(self, safe_mult, proposed=None, uniforms=None):
+        """global_update (global_updates.jl:203-219) for every chain.  proposed: (N, M, B) int8 configurations or
+        None for GlobalFlip.  -> (accepted[B] in {0, 1}, p[B])."""
+        acc = np.zeros(self.B, dtype=np.int64)
+        probs = np.zeros(self.B)
+        pc = uu = None
+        if proposed is not None:
+            proposed = np.asfortranarray(proposed, dtype=np.int8)
+            assert proposed.shape == (self.N, self.M, self.B)
+            pc = proposed.ctypes.data_as(_lib.i8p)
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+            assert uniforms.shape == (self.B,)
+            uu = _dp(uniforms)
+        self._ck(self._L.dqmc_global_update(self._h, pc, uu, int(safe_mult), acc.ctypes.data_as(_lib.i64p), _dp(probs)))
+        return acc, probs
+
     def set_sweep_index(self, s):
         self._ck(self._L.dqmc_set_sweep_index(self._h, int(s)))
 

@@ -132,8 +132,9 @@ cudaError_t ident(dqmc_ctx* c, double* A) { ProfScope ps(c, DQMC_PROF_OTHER); re
 cudaError_t ones(dqmc_ctx* c, double* v) { ProfScope ps(c, DQMC_PROF_OTHER); return launch_fill(v, 1.0, (long long)c->nmat * c->N, c->st); }
 
 
-// calculate_greens_AVX! (stack.jl:442-496); destroys Ul, Dl, Tl, Ur, Dr, Tr like the reference.
-static cudaError_t calculate_greens(dqmc_ctx* c, double* G)
+// First half of calculate_greens_AVX! (stack.jl:442-480) == calculate_inv_greens_udt
+// (updates/global_updates.jl:25-52): afterwards G^-1 = Tl Ul Dr Tr Ur^-1 with det(G) = 1 / prod(Dr).
+cudaError_t calculate_inv_greens_udt(dqmc_ctx* c, double* G)
 {
     // G = Dl (Tl Tr') Dr                                            :450-452
     CE(mm(c, G, c->Tl, false, false, c->Tr, true, false, vec_scale(c, c->Dl), no_scale(), vec_scale(c, c->Dr)));
@@ -143,11 +144,20 @@ static cudaError_t calculate_greens(dqmc_ctx* c, double* G)
     CE(rdivp(c, c->Ur, G, c->Ul));                                   // Ur = Ur / G         :465
     // Tr = Tl' Ur + Diagonal(Dr)                                    :466, 472
     CE(mm(c, c->Tr, c->Tl, true, false, c->Ur, false, false, no_scale(), no_scale(), no_scale(), c->Dr));
-    CE(udt(c, c->Tr, no_scale(), c->Ul, c->Dr, c->Tr, false));       // :480
+    return udt(c, c->Tr, no_scale(), c->Ul, c->Dr, c->Tr, false);    // :480
+}
+
+// calculate_greens_AVX! (stack.jl:442-496); destroys Ul, Dl, Tl, Ur, Dr, Tr like the reference.
+cudaError_t calculate_greens(dqmc_ctx* c, double* G)
+{
+    CE(calculate_inv_greens_udt(c, G));
     CE(rdivp(c, c->Ur, c->Tr, G));                                   // :481
     CE(mm(c, c->Tr, c->Tl, false, false, c->Ul, false, false));      // Tr = Tl Ul          :482
     // G = (Ur Diagonal(1 / Dr)) Tr'                                 :486-493
     CE(mm(c, G, c->Ur, false, false, c->Tr, true, false, no_scale(), vec_scale(c, c->Dr, true)));
+    // the reference leaves 1 / Dr in Dl (:486), which propose_global_from_conf reads as det(G)
+    // (global_updates.jl:151-154); Ul..Tr are scratch for the measurement code, so keep a copy
+    if (G == c->greens) CE(copy_vecs(c, c->Dgreens, c->Dr));
     return cudaSuccess;
 }
 
@@ -182,7 +192,7 @@ static cudaError_t add_slice_sequence_right(dqmc_ctx* c, int idx)
     return mm(c, slot_mat(c, c->t_stack, idx - 1), c->tmp1, false, false, slot_mat(c, c->t_stack, idx), false, false);
 }
 
-static cudaError_t load_udt(dqmc_ctx* c, double* U, double* D, double* T, int slot)   // slot < 0 -> identity
+cudaError_t load_udt(dqmc_ctx* c, double* U, double* D, double* T, int slot)   // slot < 0 -> identity
 {
     if (slot < 0) { CE(ident(c, U)); CE(ones(c, D)); return ident(c, T); }
     CE(copy_mats(c, U, slot_mat(c, c->u_stack, slot)));
@@ -203,6 +213,33 @@ static cudaError_t prop_check(dqmc_ctx* c)
                              c->stats_prop, c->st);
 }
 
+// One side of calculate_greens(mc, slice) (stack.jl:525-583) / inv_det (global_updates.jl:70-137): the UDT
+// form of B_slice ... B_1 (dagger == false) or of (B_M ... B_{slice+1})^T (dagger == true), stabilised
+// whenever k % safe_mult == 0.
+cudaError_t build_chain_udt(dqmc_ctx* c, int slice, int safe_mult, bool dagger, double* U, double* D, double* T)
+{
+    CE(load_udt(c, U, D, T, -1));
+    double* cur = c->curr_U; double* oth = c->tmp2;
+    CE(ident(c, cur));
+    auto stabilise = [&](double* Uout) -> cudaError_t {
+        CE(udt(c, cur, vec_scale(c, D), Uout, D, c->tmp1, true));
+        CE(copy_mats(c, c->greens_temp, T));
+        return mm(c, T, c->tmp1, false, false, c->greens_temp, false, false);
+    };
+    if (dagger) {
+        for (int k = c->M; k >= slice + 1; --k) {
+            CE(slice_daggered_left(c, oth, cur, k)); std::swap(cur, oth);
+            if (k % safe_mult == 0) { CE(stabilise(oth)); std::swap(cur, oth); }
+        }
+    } else {
+        for (int k = 1; k <= slice; ++k) {
+            CE(slice_left(c, oth, cur, k)); std::swap(cur, oth);
+            if (k % safe_mult == 0) { CE(stabilise(oth)); std::swap(cur, oth); }
+        }
+    }
+    return stabilise(U);
+}
+
 // build_stack (stack.jl:257-281)
 static cudaError_t forward_build(dqmc_ctx* c)
 {
@@ -215,7 +252,7 @@ static cudaError_t forward_build(dqmc_ctx* c)
 }
 
 // reverse_build_stack (stack.jl:284-308)
-static cudaError_t reverse_build(dqmc_ctx* c)
+cudaError_t reverse_build(dqmc_ctx* c)
 {
     CE(clear_slot(c, c->C));
     for (int i = c->C; i >= 1; --i) CE(add_slice_sequence_right(c, i));
@@ -226,7 +263,7 @@ static cudaError_t reverse_build(dqmc_ctx* c)
 }
 
 // propagate (stack.jl:605-730)
-static cudaError_t propagate(dqmc_ctx* c)
+cudaError_t propagate(dqmc_ctx* c)
 {
     c->current_slice += c->direction;
     if (c->direction == 1) {
@@ -408,7 +445,7 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     A_(u_stack, mat * (c->C + 1)); A_(t_stack, mat * (c->C + 1)); A_(d_stack, vec * (c->C + 1));
     A_(greens, mat); A_(greens_temp, mat); A_(Ul, mat); A_(Ur, mat); A_(Tl, mat); A_(Tr, mat);
     A_(tmp1, mat); A_(tmp2, mat); A_(curr_U, mat); A_(Vwork, (size_t)c->nmat * c->ldv * c->N);
-    A_(Dl, vec); A_(Dr, vec); A_(tau, vec);
+    A_(Dl, vec); A_(Dr, vec); A_(tau, vec); A_(Dgreens, vec);
     A_(udt_scratch, (size_t)c->nmat * udt_reg_scratch_doubles(c->N, c->ld));
     A_(udt_iscratch, (size_t)c->nmat * udt_reg_scratch_ints(c->N));
     A_(pivot, vec); A_(accepted, (size_t)c->B);
@@ -635,28 +672,7 @@ int32_t dqmc_calculate_greens_at(dqmc_ctx* c, int32_t slice, int32_t safe_mult, 
 {
     ENTER(c);
     if (!G || slice < 0 || slice > c->M || safe_mult < 1) FAIL(c, DQMC_ERR_INVALID, "dqmc_calculate_greens_at: bad arguments");
-    auto chain = [&](bool dagger, double* U, double* D, double* T) -> cudaError_t {
-        CE(load_udt(c, U, D, T, -1));
-        double* cur = c->curr_U; double* oth = c->tmp2;
-        CE(ident(c, cur));
-        auto stabilise = [&](double* Uout) -> cudaError_t {
-            CE(udt(c, cur, vec_scale(c, D), Uout, D, c->tmp1, true));
-            CE(copy_mats(c, c->greens_temp, T));
-            return mm(c, T, c->tmp1, false, false, c->greens_temp, false, false);
-        };
-        if (dagger) {
-            for (int k = c->M; k >= slice + 1; --k) {
-                CE(slice_daggered_left(c, oth, cur, k)); std::swap(cur, oth);
-                if (k % safe_mult == 0) { CE(stabilise(oth)); std::swap(cur, oth); }
-            }
-        } else {
-            for (int k = 1; k <= slice; ++k) {
-                CE(slice_left(c, oth, cur, k)); std::swap(cur, oth);
-                if (k % safe_mult == 0) { CE(stabilise(oth)); std::swap(cur, oth); }
-            }
-        }
-        return stabilise(U);
-    };
+    auto chain = [&](bool dagger, double* U, double* D, double* T) { return build_chain_udt(c, slice, safe_mult, dagger, U, D, T); };
     if (slice + 1 <= c->M) CK(c, chain(true, c->Ur, c->Dr, c->Tr)); else CK(c, load_udt(c, c->Ur, c->Dr, c->Tr, -1));
     if (slice >= 1) CK(c, chain(false, c->Ul, c->Dl, c->Tl)); else CK(c, load_udt(c, c->Ul, c->Dl, c->Tl, -1));
     CK(c, calculate_greens(c, c->greens_temp));
@@ -800,6 +816,7 @@ static int32_t make_op_ctx(int device, int n, int batch, dqmc_ctx** out)
     if (e == cudaSuccess) e = dalloc(c, &c->Dl, vec);
     if (e == cudaSuccess) e = dalloc(c, &c->Dr, vec);
     if (e == cudaSuccess) e = dalloc(c, &c->tau, vec);
+    if (e == cudaSuccess) e = dalloc(c, &c->Dgreens, vec);
     if (e == cudaSuccess) e = dalloc(c, &c->pivot, vec);
     if (e == cudaSuccess) e = dalloc(c, &c->udt_scratch, (size_t)c->nmat * udt_reg_scratch_doubles(n, c->ld));
     if (e == cudaSuccess) e = dalloc(c, &c->udt_iscratch, (size_t)c->nmat * udt_reg_scratch_ints(n));

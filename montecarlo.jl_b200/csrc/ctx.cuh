@@ -30,6 +30,8 @@ struct dqmc_ctx {
     double *u_stack = nullptr, *d_stack = nullptr, *t_stack = nullptr;
     double *greens = nullptr, *greens_temp = nullptr, *Ul = nullptr, *Ur = nullptr, *Tl = nullptr, *Tr = nullptr;
     double *tmp1 = nullptr, *tmp2 = nullptr, *curr_U = nullptr, *Dl = nullptr, *Dr = nullptr;
+    double* Dgreens = nullptr;         // D of the last Green's function calculation: det(greens) = 1 / prod(Dgreens)
+    int8_t* conf_backup = nullptr;     // temp_conf of the global updates (fields.jl: temp_conf)
     double *Vwork = nullptr, *tau = nullptr, *udt_scratch = nullptr;
     int* pivot = nullptr; int* udt_iscratch = nullptr;
     int* accepted = nullptr;
@@ -119,5 +121,11 @@ cudaError_t copy_mats(dqmc_ctx* c, double* dst, const double* src);
 cudaError_t copy_vecs(dqmc_ctx* c, double* dst, const double* src);
 cudaError_t ident(dqmc_ctx* c, double* A);
 cudaError_t ones(dqmc_ctx* c, double* v);
+cudaError_t load_udt(dqmc_ctx* c, double* U, double* D, double* T, int slot);   // slot < 0 -> identity
+cudaError_t build_chain_udt(dqmc_ctx* c, int slice, int safe_mult, bool dagger, double* U, double* D, double* T);
+cudaError_t calculate_inv_greens_udt(dqmc_ctx* c, double* G);
+cudaError_t calculate_greens(dqmc_ctx* c, double* G);
+cudaError_t reverse_build(dqmc_ctx* c);
+cudaError_t propagate(dqmc_ctx* c);
 void ut_destroy(dqmc_ctx* c);     // ut.cu
 void meas_destroy(dqmc_ctx* c);   // measure.cu

@@ -540,6 +540,205 @@ udt_formq_kernel(const UdtParams p, int cols_per_cta)
 }
 
 // ================================================================================================
+// explicit Q, blocked: four reflectors at a time in compact WY form,
+//     H_k H_{k+1} H_{k+2} H_{k+3} = I - V T V^T   (T 4 x 4 upper triangular, LAPACK dlarft "forward, columnwise").
+// The per-reflector kernel above is bound by its dependent chain (dots -> shuffle tree -> update) once per
+// reflector; here one tree serves four reflectors and the 32 dot-product chains of a warp are independent,
+// so the kernel runs at the FP64 pipe instead of at shuffle latency.  The four Householder vectors of a
+// block are staged once per CTA in shared memory (cp.async, double buffered) instead of once per warp from L2.
+// ================================================================================================
+
+// T factors of every block of four reflectors: T4[mat][g][j + 4 * i] = T[j][i]
+__global__ void __launch_bounds__(128)
+udt_wy_t_kernel(const UdtParams p, double* __restrict__ T4, int ngroups)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= p.batch * ngroups) return;
+    const int mat = gw / ngroups, g = gw - mat * ngroups;
+    const int n = p.n, ldv = p.ldv;
+    const double* Vg = p.Vwork + (long long)mat * p.strideV;
+    const double* tg = p.tau + (long long)mat * p.strideTau;
+    double s01 = 0, s02 = 0, s03 = 0, s12 = 0, s13 = 0, s23 = 0;
+    const int k0 = 4 * g;
+    for (int row = k0 + lane; row < ldv; row += 32) {           // vectors are zero above their own index
+        double v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (k0 + j < n) ? Vg[(long long)(k0 + j) * ldv + row] : 0.0;
+        s01 = fma(v[0], v[1], s01); s02 = fma(v[0], v[2], s02); s03 = fma(v[0], v[3], s03);
+        s12 = fma(v[1], v[2], s12); s13 = fma(v[1], v[3], s13); s23 = fma(v[2], v[3], s23);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s01 += __shfl_xor_sync(0xffffffffu, s01, o); s02 += __shfl_xor_sync(0xffffffffu, s02, o);
+        s03 += __shfl_xor_sync(0xffffffffu, s03, o); s12 += __shfl_xor_sync(0xffffffffu, s12, o);
+        s13 += __shfl_xor_sync(0xffffffffu, s13, o); s23 += __shfl_xor_sync(0xffffffffu, s23, o);
+    }
+    if (lane == 0) {
+        double t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = (k0 + j < n) ? tg[k0 + j] : 0.0;
+        double T[4][4] = {};
+        T[0][0] = t[0]; T[1][1] = t[1]; T[2][2] = t[2]; T[3][3] = t[3];
+        T[0][1] = -t[1] * (T[0][0] * s01);
+        T[0][2] = -t[2] * (T[0][0] * s02 + T[0][1] * s12);
+        T[1][2] = -t[2] * (T[1][1] * s12);
+        T[0][3] = -t[3] * (T[0][0] * s03 + T[0][1] * s13 + T[0][2] * s23);
+        T[1][3] = -t[3] * (T[1][1] * s13 + T[1][2] * s23);
+        T[2][3] = -t[3] * (T[2][2] * s23);
+        double* out = T4 + ((long long)mat * ngroups + g) * 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j + 4 * i] = T[j][i];
+    }
+}
+
+__device__ __forceinline__ void cp_async16_q(void* smem, const void* gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gmem));
+}
+
+template <int RPL>
+__global__ void __launch_bounds__(256)
+udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
+{
+    constexpr int NV = RPL * 32;
+    const int n = p.n, ld = p.ld, ldv = p.ldv;
+    const int ctas_per_mat = (n + 63) / 64;
+    const int mat = blockIdx.x / ctas_per_mat, part_i = blockIdx.x - mat * ctas_per_mat;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col0 = part_i * 64 + warp * 8;             // this warp owns columns col0 .. col0 + 7
+    const double* Vg = p.Vwork + (long long)mat * p.strideV;
+    const double* Tg = T4 + (long long)mat * ngroups * 16;
+    double* Ug = p.U + (long long)mat * p.strideU;
+
+    __shared__ __align__(16) double vs[2][4][NV];
+    __shared__ double ts[2][16];
+
+    double a[8][RPL];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) a[c][r] = (col0 + c < n && lane + 32 * r == col0 + c) ? 1.0 : 0.0;
+
+    const int ctop = min(n, part_i * 64 + 64) - 1;       // highest column of this CTA
+    const int gtop = ctop >> 2;
+    const int wtop = (col0 < n) ? (min(n - 1, col0 + 7) >> 2) : -1;   // highest block that touches this warp
+    const bool dense = (ldv == NV);
+    auto stage = [&](int g, int s) {                     // block g -> vs[s], ts[s]
+        for (int e = tid; e < 4 * (NV / 2); e += 256) {
+            const int j = e / (NV / 2), r2 = (e - j * (NV / 2)) * 2;
+            const int k = 4 * g + j;
+            if (k < n && (dense || r2 + 1 < ldv)) cp_async16_q(&vs[s][j][r2], Vg + (long long)k * ldv + r2);
+            else { vs[s][j][r2] = 0.0; vs[s][j][r2 + 1] = 0.0; }
+        }
+        if (tid < 16) ts[s][tid] = Tg[(long long)g * 16 + tid];
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    stage(gtop, 0);
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    for (int g = gtop; g >= 0; --g) {
+        const int s = (gtop - g) & 1;
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();                                 // block g visible; everybody is done with block g + 1
+        if (g > 0) stage(g - 1, s ^ 1);
+        if (g > wtop) continue;                          // warp-uniform
+        const int r0 = (4 * g) >> 5;                     // first register row a reflector of this block touches
+        // ---- W = V^T A: 32 independent chains ---------------------------------------------------
+        double d[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) d[j][c] = 0.0;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            if (r >= r0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double v = vs[s][j][lane + 32 * r];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) d[j][c] = fma(v, a[c][r], d[j][c]);
+                }
+            }
+        // ---- one reduction tree for the whole block: halve over the columns, butterfly over the rest --
+        double y1[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double send = h16 ? d[j][c] : d[j][c + 4];
+                const double keep = h16 ? d[j][c + 4] : d[j][c];
+                y1[j][c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+        double y2[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const double send = h8 ? y1[j][c] : y1[j][c + 2];
+                const double keep = h8 ? y1[j][c + 2] : y1[j][c];
+                y2[j][c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+        double w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double send = h4 ? y2[j][0] : y2[j][1];
+            const double keep = h4 ? y2[j][1] : y2[j][0];
+            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] += __shfl_xor_sync(0xffffffffu, w[j], 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] += __shfl_xor_sync(0xffffffffu, w[j], 1);
+        // ---- Y = T W for the column this lane ended up with (col_of_lane) ------------------------
+        double y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = j; i < 4; ++i) acc = fma(ts[s][j + 4 * i], w[i], acc);
+            y[j] = acc;
+        }
+        // ---- A -= V Y, four columns at a time (register budget) ------------------------------------
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            double yy[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int cc = half * 4 + c;
+                const int src = ((cc & 4) ? 16 : 0) | ((cc & 2) ? 8 : 0) | ((cc & 1) ? 4 : 0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) yy[j][c] = -__shfl_sync(0xffffffffu, y[j], src);
+            }
+#pragma unroll
+            for (int r = 0; r < RPL; ++r)
+                if (r >= r0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double v = vs[s][j][lane + 32 * r];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) a[half * 4 + c][r] = fma(v, yy[j][c], a[half * 4 + c][r]);
+                    }
+                }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int col = col0 + c;
+        if (col < n) {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const int row = lane + 32 * r;
+                if (row < n) Ug[row + (long long)col * ld] = a[c][r];
+            }
+        }
+    }
+}
+
+// ================================================================================================
 // host side
 // ================================================================================================
 template <int RPL>
@@ -556,6 +755,21 @@ static cudaError_t launch_steps(const UdtParams& p, const UdtLevel& g, cudaStrea
     cfg.attrs = at; cfg.numAttrs = 1;
     ++g_kernel_launches;
     return cudaLaunchKernelEx(&cfg, udt_steps_kernel<RPL>, p, g);
+}
+
+template <int RPL>
+static cudaError_t launch_formq4(const UdtParams& p, double* T4, cudaStream_t st)
+{
+    const int ngroups = (p.n + 3) / 4;
+    const int warps = p.batch * ngroups;
+    ++g_kernel_launches;
+    udt_wy_t_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(p, T4, ngroups);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int ctas = p.batch * ((p.n + 63) / 64);
+    ++g_kernel_launches;
+    udt_formq4_kernel<RPL><<<(unsigned)ctas, 256, 0, st>>>(p, T4, ngroups);
+    return cudaGetLastError();
 }
 
 template <int RPL>
@@ -597,6 +811,7 @@ size_t udt_reg_scratch_doubles(int n, int ld)
 {
     size_t tot = (size_t)ld * n + 64;
     for (int nk = udt_next_level_size(n); nk > 0; nk = udt_next_level_size(nk)) tot += (size_t)((nk + 1) & ~1) * nk;
+    tot += (size_t)((n + 3) / 4) * 16;                   // T factors of the blocked form-Q
     return tot;
 }
 size_t udt_reg_scratch_ints(int n) { return (size_t)2 * n + 16; }
@@ -640,7 +855,10 @@ cudaError_t launch_udt_reg(const UdtParams& p, cudaStream_t st)
     }
     // Q
     const int rpl = (n + 31) / 32;
-    DQMC_RPL_SWITCH(rpl, (launch_formq<R>(p, st)))
+    static const bool formq_v1 = getenv("DQMC_UDT_FORMQ_V1") != nullptr;     // A/B knob: per-reflector kernel
+    double* T4 = S_base + s_off;                         // behind the trailing-block buffers
+    if (formq_v1) { DQMC_RPL_SWITCH(rpl, (launch_formq<R>(p, st))) }
+    else { DQMC_RPL_SWITCH(rpl, (launch_formq4<R>(p, T4, st))) }
     if (err != cudaSuccess) return err;
     // the Val(false) form wants the columns of D^-1 R in pivot (logical) order
     if (!direct_T)

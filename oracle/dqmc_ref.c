@@ -901,3 +901,6 @@ double ref_run_chains(ref_chain **chains, int nchains, int nthreads, int warm, i
 
 /* unequal-time Green's functions: UnequalTimeStack + CombinedGreensIterator */
 #include "dqmc_ref_ut.inc.c"
+
+/* global Metropolis updates */
+#include "dqmc_ref_global.inc.c"

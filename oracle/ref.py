@@ -34,7 +34,7 @@ def build(force: bool = False) -> Path:
     so = _HERE / "libdqmc_ref.so"
     src = _HERE / "dqmc_ref.c"
     hdr = _HERE.parent / "include" / "dqmc_rng.h"
-    deps = [src, _HERE / "dqmc_ref_ut.inc.c", hdr]
+    deps = [src, _HERE / "dqmc_ref_ut.inc.c", _HERE / "dqmc_ref_global.inc.c", hdr]
     stale = (not so.exists()) or so.stat().st_mtime < max(d.stat().st_mtime for d in deps)
     if force or stale:
         subprocess.check_call(["make", "-C", str(_HERE), "-B", "libdqmc_ref.so"],
@@ -92,6 +92,8 @@ def lib():
         L.ref_cgi_first.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
         L.ref_cgi_next.restype = C.c_int
         L.ref_cgi_next.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]
+        L.ref_global_update.restype = C.c_int
+        L.ref_global_update.argtypes = [C.c_void_p, c_i8_p, C.c_double, C.c_int, c_double_p]
         _LIB = L
     return _LIB
 
@@ -326,6 +328,15 @@ class RefChain:
         while nxt >= 0:
             yield (nxt - 1, *[b.copy() for b in bufs])
             nxt = lib().ref_cgi_next(self._h, nxt, *[_dp(b) for b in bufs])
+
+    def global_update(self, new_conf, uniform=0.5, safe_mult=None):
+        """global_update (global_updates.jl:203-219) with the proposed configuration -> (accepted, p)."""
+        nc = np.asfortranarray(new_conf, dtype=np.int8)
+        assert nc.shape == (self.N, self.M)
+        p = C.c_double(0.0)
+        acc = lib().ref_global_update(self._h, nc.ctypes.data_as(c_i8_p), float(uniform),
+                                      int(safe_mult or self.safe_mult), C.byref(p))
+        return acc, p.value
 
     def set_sweep_index(self, s):
         lib().ref_set_sweep_index(self._h, int(s))
