@@ -67,6 +67,36 @@ def run_cpu(cfg, steps, warmup, max_chains=None):
             "acceptance": a, "N": N, "M": M, "nb": chains[0].nb, "C": chains[0].C}
 
 
+def run_cpu_measure(cfg):
+    """The oracle's CPU time for one TimeIntegral measurement pass (CombinedGreensIterator + Wick kernels), one
+    chain per host core."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import measure as OMS, model as OM, ref as OR
+    kind, Ls, U, beta, _, desc = build_model(cfg)
+    T = OM.hopping_matrix(kind, Ls)
+    N, M = T.shape[0], OM.n_slices(beta, DELTA_TAU)
+    cores = OR.lib().ref_max_threads()
+    g = np.random.default_rng(SEED)
+    chains = [OR.RefChain(T, U=U, beta=beta, delta_tau=DELTA_TAU, safe_mult=SAFE_MULT, seed=SEED, chain_id=b,
+                          conf=np.asfortranarray(g.choice(np.array([-1, 1], dtype=np.int8), size=(N, M))))
+              for b in range(cores)]
+    s2d, nbasis = OMS.bravais_srctrg2dir(Ls), OM.UNIT_CELLS[kind][0]
+
+    def one(c):
+        c.init()
+        t0 = time.time()
+        G00 = c.measured_greens()
+        OMS.time_integral(G00, c.combined_greens_iterator(), c.delta_tau, c.M, s2d, nbasis)
+        return time.time() - t0
+
+    t0 = time.time()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        per = list(ex.map(one, chains))
+    return {"time_integral_s_per_chain": float(np.mean(per)), "cores": cores, "chains": cores, "wall_s": time.time() - t0,
+            "time_integral_passes_per_s": cores / float(np.max(per)), "kind": "port",
+            "sample": f"{cores} chains (one per host core), one TimeIntegral pass each; oracle C iterator + numpy Wick kernels"}
+
+
 # ------------------------------------------------------------------------------------------
 # clocks sampler
 # ------------------------------------------------------------------------------------------
@@ -126,6 +156,9 @@ def main():
     ap.add_argument("--delay-block", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--measure", action="store_true",
+                    help="also time one equal-time + one TimeIntegral measurement pass (device Wick kernels and the "
+                         "CombinedGreensIterator) and the oracle's CPU time for the same; default for cfg5")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -277,6 +310,32 @@ def main():
                     "kernel_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
                     "whole_sweep_frac_of_fp64_peak": (flops_per_sweep(N, M, C, nb, acc_rate) * value / world / 1e12) / p64 if p64 else None}
 
+    # ---------------- measurement pass (cfg5's equal-time + unequal-time clause) ----------------
+    meas = None
+    if args.measure or args.config == "cfg5":
+        from oracle import measure as OMS      # lattice tables only (inputs)
+        nbasis = OM.UNIT_CELLS[kind][0]
+        ctx.set_lattice(OMS.bravais_srctrg2dir(Ls), nbasis, T, U)
+        ctx.measure_equal_time(); ctx.measure_time_integral(SAFE_MULT, DELTA_TAU)          # warm-up
+        l1 = ctx.kernel_launches()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        barrier()
+        ev[0].record(stream)
+        ctx.measure_equal_time()
+        ev[1].record(stream)
+        ctx.measure_time_integral(SAFE_MULT, DELTA_TAU)
+        ev[2].record(stream)
+        barrier()
+        t_et, t_ti = max_over_ranks(ev[0].elapsed_time(ev[1])), max_over_ranks(ev[1].elapsed_time(ev[2]))
+        rate = 10                                                                         # DQMC.jl:37 measure_rate
+        meas = {"equal_time_ms": t_et, "time_integral_ms": t_ti, "chains_per_gpu": B, "gpu_launches": int(ctx.kernel_launches() - l1),
+                "observables": "occupation, kinetic/interaction/total energy, CDC, SDC x/y/z (equal time); CDS, SDS x/y/z "
+                               "(TimeIntegral over the CombinedGreensIterator, recalculate = 2 safe_mult)",
+                "sweeps_per_s_with_measurements": world * B * rate / ((rate * ms / K + t_et + t_ti) * 1e-3),
+                "measure_rate": rate}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            meas["cpu"] = run_cpu_measure(args.config)
+
     line = None
     if rank == 0:
         line = {"metric": "DQMC sweeps/sec (all chains)", "value": value, "unit": "sweeps/s", "n_gpus": world,
@@ -291,6 +350,8 @@ def main():
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K},
                 "roofline": roof,
                 "flops_per_sweep_per_chain": flops_per_sweep(N, M, C, nb, acc_rate)}
+        if meas is not None:
+            line["measurement"] = meas
         if world == 1 and not args.no_cpu_baseline:
             r = run_cpu(args.config, 1, 0)
             line["cpu_baseline"] = {"value": r["value"], "unit": "sweeps/s", "cores": r["cores"], "kind": "port",

@@ -157,11 +157,105 @@ def greens_measurement(mc, model=None):
     return GreensMeasurement(mc)
 
 
+class DeviceMeasurement:
+    """A DQMCMeasurement (measurements/generic.jl:1-120) whose Wick kernel runs on the device
+    (csrc/measure.cu).  `key` names the observable of Context.OBS_NAMES; `time_integral` marks the
+    TimeIntegral greens iterator (susceptibilities), otherwise Greens() (equal time).  Every measurement
+    pushes one value per chain into a {count, sum, sum of squares} accumulator (LogBinner stand-in)."""
+
+    def __init__(self, key: str, time_integral: bool):
+        self.key, self.time_integral = key, time_integral
+        self.count, self.sum, self.sumsq = 0, None, None
+
+    def push(self, values):
+        values = np.asarray(values, dtype=np.float64)
+        if self.sum is None:
+            self.sum, self.sumsq = np.zeros_like(values), np.zeros_like(values)
+        self.count += 1
+        self.sum += values
+        self.sumsq += values * values
+
+    def mean(self, chain=None):
+        m = self.sum / max(self.count, 1)
+        return m.mean(axis=0) if chain is None else m[chain]
+
+    def std_error(self):
+        n = self.count * self.sum.shape[0]
+        mean = self.sum.sum(axis=0) / n
+        var = np.maximum(self.sumsq.sum(axis=0) / n - mean ** 2, 0.0)
+        return np.sqrt(var / max(n - 1, 1))
+
+
+# constructors with the reference's names (measurements/constructors/*.jl)
+def occupation(mc, model=None):
+    return DeviceMeasurement("occ", False)
+
+
+def kinetic_energy(mc, model=None):
+    return DeviceMeasurement("K", False)
+
+
+def interaction_energy(mc, model=None):
+    return DeviceMeasurement("V", False)
+
+
+def total_energy(mc, model=None):
+    return DeviceMeasurement("E", False)
+
+
+def charge_density_correlation(mc, model=None):
+    return DeviceMeasurement("cdc", False)
+
+
+def charge_density_susceptibility(mc, model=None):
+    return DeviceMeasurement("cds", True)
+
+
+def spin_density_correlation(mc, model=None, dir="z"):
+    return DeviceMeasurement({"x": "sdxc", "y": "sdyc", "z": "sdzc"}[str(dir).lstrip(":")], False)
+
+
+def spin_density_susceptibility(mc, model=None, dir="z"):
+    return DeviceMeasurement({"x": "sdxs", "y": "sdys", "z": "sdzs"}[str(dir).lstrip(":")], True)
+
+
+# ---- updates (updates/local_updates.jl:70-84, updates/global_updates.jl:229-270, updates/scheduler.jl:236-289)
+class LocalSweep:
+    def __init__(self, N=1):
+        self.N = int(N)
+
+
+class GlobalFlip:
+    pass
+
+
+class GlobalShuffle:
+    pass
+
+
+class SimpleScheduler:
+    """SimpleScheduler(updates...): cycles through the given updates, one per sweep; LocalSweep(N) expands to N
+    local sweeps and at least one local sweep is required (scheduler.jl:267-278)."""
+
+    def __init__(self, *updates):
+        seq = []
+        for u in updates:
+            seq.extend([LocalSweep()] * u.N if isinstance(u, LocalSweep) else [u])
+        if not any(isinstance(u, LocalSweep) for u in seq):
+            raise ValueError("The scheduler requires local updates, but none were passed (scheduler.jl:269)")
+        self.sequence, self.idx = seq, 0
+
+    def next(self):
+        u = self.sequence[self.idx]
+        self.idx = (self.idx + 1) % len(self.sequence)
+        return u
+
+
 class DQMC:
     """DQMC(model; beta, delta_tau, safe_mult, thermalization, sweeps, measure_rate, seed, field, ...)."""
 
     def __init__(self, model: HubbardModel, *, seed=-1, field=None, n_chains=1, device=0, chain_offset=0,
-                 delay_block=0, **kwargs):
+                 delay_block=0, scheduler=None, recalculate=None, **kwargs):
         self.model = model
         self.parameters = DQMCParameters(**kwargs)
         self._rng = np.random.default_rng(None if seed == -1 else seed)
@@ -187,6 +281,11 @@ class DQMC:
             check_propagation_error=self.parameters.check_propagation_error,
             seed=(1234 if seed == -1 else seed), chain_offset=chain_offset, device=device, delay_block=delay_block)
         self.stack = _StackView(self)
+        self.scheduler = scheduler or SimpleScheduler(LocalSweep())
+        self.recalculate = recalculate          # CombinedGreensIterator's recalculate (default 2 safe_mult)
+        self.global_accepted = np.zeros(n_chains, dtype=np.int64)
+        self.global_total = 0
+        self._lattice_set = False
         self._initialized = False
 
     # mc[:G] = greens_measurement(mc, model)   (Measurements.jl:318-323)
@@ -203,12 +302,60 @@ class DQMC:
         self._initialized = True
 
     def sweep_once(self, uniforms=None):
-        """sweep_once! (DQMC.jl:200-225) without the measurement hand-off."""
-        acc = self.ctx.sweep(1, uniforms)
-        self.accepted += acc
-        self.total += 2 * self.ctx.N * self.ctx.M
+        """sweep_once! (DQMC.jl:200-225) without the measurement hand-off: one update of the scheduler."""
+        u = self.scheduler.next()
         self.last_sweep += 1
-        return acc / (2 * self.ctx.N * self.ctx.M)
+        if isinstance(u, LocalSweep):
+            acc = self.ctx.sweep(1, uniforms)
+            self.accepted += acc
+            self.total += 2 * self.ctx.N * self.ctx.M
+            return acc / (2 * self.ctx.N * self.ctx.M)
+        proposed = None
+        if isinstance(u, GlobalShuffle):                       # global_updates.jl:262-270: shuffle!(conf)
+            conf = self.ctx.get_conf()
+            proposed = np.asfortranarray(np.stack(
+                [self._rng.permutation(conf[:, :, b].ravel()).reshape(conf.shape[:2]) for b in range(self.ctx.B)], axis=2))
+        acc, _ = self.ctx.global_update(self.parameters.safe_mult, proposed=proposed)
+        self.global_accepted += acc
+        self.global_total += 1
+        return acc.astype(np.float64)
+
+    # ---- unequal-time Green's functions (unequal_time_stack.jl, measurements/greens_iterators.jl)
+    def greens_kl(self, k, l, chain=None):
+        """greens(mc, k, l): G(k <- l), 0 <= k, l <= slices."""
+        g = self.ctx.ut_greens(k, l)
+        g = g[:, :, :, 0] if chain is None else g[:, :, :, chain]
+        return g[:, :, 0] if self.ctx.nb == 1 else g
+
+    def combined_greens_iterator(self, recalculate=None, start=0, stop=None):
+        """CombinedGreensIterator(mc; recalculate, start, stop): yields (l, G0l, Gl0, Gll) for all chains."""
+        return self.ctx.combined_greens_iterator(self.parameters.safe_mult, recalculate or self.recalculate, start, stop)
+
+    def _set_lattice(self):
+        if not self._lattice_set:
+            l = self.model.l
+            self.ctx.set_lattice(np.array(l.bravais_srctrg2dir(), dtype=np.int32), len(l.unitcell.sites),
+                                 self.hopping_matrix, self.model.U)
+            self._lattice_set = True
+
+    def measure(self):
+        """The measurement hand-off of sweep_once! (DQMC.jl:217-221): one equal-time and/or one TimeIntegral pass
+        on the device, then every registered measurement is pushed its per-chain values."""
+        dev = [m for m in self.measurements.values() if isinstance(m, DeviceMeasurement)]
+        if dev:
+            self._set_lattice()
+            if any(not m.time_integral for m in dev):
+                self.ctx.measure_equal_time()
+            if any(m.time_integral for m in dev):
+                self.ctx.measure_time_integral(self.parameters.safe_mult, self.parameters.delta_tau, self.recalculate)
+            vals = self.ctx.measurements()
+            for m in dev:
+                m.push(vals[m.key])
+        others = [m for m in self.measurements.values() if not isinstance(m, DeviceMeasurement)]
+        if others:
+            G = self.ctx.measured_greens()
+            for m in others:
+                m.push(G)
 
     def greens(self, chain=None):
         """greens(mc) (greens.jl:94-125): exp(+dtau T / 2) G_eff exp(-dtau T / 2)."""
@@ -234,9 +381,7 @@ def run(mc: DQMC, *, verbose=False, min_update_rate=0.001):
     for i in range(mc.last_sweep + 1, total + 1):
         mc.sweep_once()
         if i > p.thermalization and (i - p.thermalization) % p.measure_rate == 0 and mc.measurements:
-            G = mc.ctx.measured_greens()
-            for m in mc.measurements.values():
-                m.push(G)
+            mc.measure()
         if verbose and i % p.print_rate == 0:
             rate = mc.accepted.sum() / max(mc.total * mc.ctx.B, 1)
             print(f"\t{i}\n\t\tsweep dur: {(time.time() - t0) / i:.3f}s\n\t\tacc rate (local): {rate:.3f}")

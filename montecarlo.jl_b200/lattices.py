@@ -49,6 +49,20 @@ class Lattice:
             f *= L
         return Bond(flat + (b.frm - 1) * f, flat_out + (b.to - 1) * f, b.uc_shift, b.label)
 
+    def bravais_srctrg2dir(self):
+        """l[:Bravais_srctrg2dir] (lattices/lattice_cache.jl:69-78, 224-240), 0-based: the direction of the
+        pair (src, trg) of Bravais cells is the flat index of mod(trg - src, Ls), x fastest."""
+        n = prod(self.Ls)
+        out = [[0] * n for _ in range(n)]
+        for src in range(n):
+            for trg in range(n):
+                d, f, a, b = 0, 1, src, trg
+                for L in self.Ls:
+                    d += f * (((b % L) - (a % L)) % L)
+                    a //= L; b //= L; f *= L
+                out[src][trg] = d
+        return out
+
     def bonds(self, directed: bool = False):
         """bonds(l, Val(directed)): Bravais cell major, unit-cell bond minor."""
         ucb = self.unitcell.bonds

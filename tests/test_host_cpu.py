@@ -96,3 +96,22 @@ def test_header_documents_reference_interfaces():
     h = (ROOT / "include" / "dqmc_b200.h").read_text()
     for cite in ("stack.jl", "local_updates.jl", "fields.jl", "greens.jl", "UDT.jl", "real.jl"):
         assert cite in h
+
+
+def test_bravais_srctrg2dir_agrees_with_oracle(b200):
+    """lattices/lattice_cache.jl:224-240"""
+    from oracle import measure as OMS
+    for ctor, Ls in ((b200.SquareLattice, (4, 4)), (b200.Honeycomb, (3, 3)), (b200.Chain, (6,))):
+        l = ctor(*Ls[:1])
+        assert np.array_equal(np.array(l.bravais_srctrg2dir()), OMS.bravais_srctrg2dir(Ls))
+    l = b200.Lattice(b200.SquareLattice(2).unitcell, (3, 4))
+    assert np.array_equal(np.array(l.bravais_srctrg2dir()), OMS.bravais_srctrg2dir((3, 4)))
+
+
+def test_simple_scheduler(b200):
+    """updates/scheduler.jl:236-289: cycles through the updates, LocalSweep(N) expands, local updates are required."""
+    with pytest.raises(ValueError):
+        b200.SimpleScheduler(b200.GlobalFlip())
+    s = b200.SimpleScheduler(b200.LocalSweep(), b200.GlobalFlip(), b200.LocalSweep(2))
+    kinds = [type(s.next()).__name__ for _ in range(8)]
+    assert kinds == ["LocalSweep", "GlobalFlip", "LocalSweep", "LocalSweep"] * 2
