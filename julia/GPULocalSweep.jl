@@ -92,4 +92,72 @@ function update(u::GPULocalSweep, mc::DQMC, model, f)
     return accepted[] / (2 * N * M)               # local_updates.jl:82
 end
 
+# ---------------------------------------------------------------------------------------------------
+# Global updates on the GPU: one more AbstractGlobalUpdate (updates/global_updates.jl:229-236).  The
+# scheduler calls update(u, mc, model, field) -> 0 / 1 like for the built-in GlobalFlip.
+# ---------------------------------------------------------------------------------------------------
+struct GPUGlobalFlip <: MonteCarlo.AbstractGlobalUpdate
+    sweep::GPULocalSweep                      # shares the context of the local sweep
+end
+name(::GPUGlobalFlip) = "GPUGlobalFlip"
+MonteCarlo.requires_temp_conf(::GPUGlobalFlip) = false     # temp_conf lives on the device
+
+function update(u::GPUGlobalFlip, mc::DQMC, model, f)
+    s = u.sweep
+    accepted = Ref{Int64}(0)
+    uniform = Ref(rand())                      # Julia keeps owning the RNG stream
+    check(s, ccall((:dqmc_global_update, LIB), Int32,
+                   (Ptr{Cvoid}, Ptr{Int8}, Ref{Float64}, Int32, Ref{Int64}, Ptr{Float64}),
+                   s.ctx, C_NULL, uniform, mc.parameters.safe_mult, accepted, C_NULL))
+    check(s, ccall((:dqmc_get_conf, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int8}), s.ctx, 0, 1, conf(f)))
+    return Int(accepted[])
+end
+
+# ---------------------------------------------------------------------------------------------------
+# Unequal-time Green's functions: a greens iterator type next to TimeIntegral / CombinedGreensIterator
+# (measurements/greens_iterators.jl:79-104, 154-196).  init(mc, it) returns an iterable whose elements are
+# the same (G0l, Gl0, Gll) GreensMatrix triples, so apply!(::TimeIntegral, ...) (generic.jl:337-372) and
+# every existing susceptibility measurement work unchanged.
+# ---------------------------------------------------------------------------------------------------
+struct GPUCombinedGreensIterator <: MonteCarlo.AbstractUnequalTimeGreensIterator
+    sweep::GPULocalSweep
+    recalculate::Int
+    start::Int
+    stop::Int
+end
+struct _GPUCGI{T <: DQMC}
+    mc::T
+    spec::GPUCombinedGreensIterator
+    bufs::NTuple{3, Array{Float64, 3}}
+end
+MonteCarlo.init(mc::DQMC, it::GPUCombinedGreensIterator) = begin
+    N = length(lattice(mc)); nb = mc.stack.greens isa MonteCarlo.BlockDiagonal ? 2 : 1
+    _GPUCGI(mc, it, ntuple(_ -> Array{Float64}(undef, N, N, nb), 3))
+end
+Base.length(it::_GPUCGI) = it.spec.stop - it.spec.start + 1
+
+function Base.iterate(it::_GPUCGI, started::Bool = false)
+    s = it.spec.sweep
+    if !started
+        check(s, ccall((:dqmc_cgi_begin, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Int32),
+                       s.ctx, it.spec.recalculate, it.spec.start, it.spec.stop, it.mc.parameters.safe_mult))
+    end
+    l = Ref{Int32}(-1)
+    check(s, ccall((:dqmc_cgi_next, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   s.ctx, l, it.bufs[1], it.bufs[2], it.bufs[3]))
+    l[] < 0 && return nothing
+    wrap(A) = size(A, 3) == 1 ? A[:, :, 1] : MonteCarlo.BlockDiagonal(A[:, :, 1], A[:, :, 2])
+    return ((MonteCarlo.GreensMatrix(0, Int(l[]), wrap(it.bufs[1])),
+             MonteCarlo.GreensMatrix(Int(l[]), 0, wrap(it.bufs[2])),
+             MonteCarlo.GreensMatrix(Int(l[]), Int(l[]), wrap(it.bufs[3]))), true)
+end
+
+# greens(mc, k, l) served by the device-side UnequalTimeStack (unequal_time_stack.jl:302-335)
+function gpu_greens(u::GPULocalSweep, mc::DQMC, k::Int, l::Int)
+    N = length(lattice(mc)); nb = mc.stack.greens isa MonteCarlo.BlockDiagonal ? 2 : 1
+    G = Array{Float64}(undef, N, N, nb)
+    check(u, ccall((:dqmc_ut_greens, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}), u.ctx, k, l, 1, G))
+    return MonteCarlo.GreensMatrix(k, l, nb == 1 ? G[:, :, 1] : MonteCarlo.BlockDiagonal(G[:, :, 1], G[:, :, 2]))
+end
+
 end # module

@@ -269,6 +269,14 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
         if (variant == 11) return launch_cfg<64, 64, 32, 32, TA, TB, 8, 3, 5>(p, st);
         if (variant == 12) return launch_cfg<64, 64, 32, 32, TA, TB, 8, 4, 5>(p, st);
         if (variant == 13) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 3, 4>(p, st);
+        if (p.M % 128 == 0 && p.N % 128 == 0) {
+            if (variant == 14) return launch_cfg<128, 128, 32, 32, TA, TB, 16, 3, 1>(p, st);   // 16 warps, 1 CTA/SM: 8.0 waves
+            if (variant == 15) return launch_cfg<128, 128, 32, 32, TA, TB, 16, 4, 1>(p, st);
+            if (variant == 16) return launch_cfg<128, 128, 64, 32, TA, TB, 16, 3, 1>(p, st);   // 8 warps of 64 x 32
+            if (variant == 17) return launch_cfg<128, 128, 32, 64, TA, TB, 16, 3, 1>(p, st);   // 8 warps of 32 x 64
+            if (variant == 18) return launch_cfg<128, 64, 32, 32, TA, TB, 16, 3, 2>(p, st);    // 8 warps, 2 CTAs/SM: 8.0 waves
+            if (variant == 19) return launch_cfg<128, 128, 32, 32, TA, TB, 8, 4, 1>(p, st);
+        }
         return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 5>(p, st);   // 2 stages, 5 CTAs/SM: best measured (28.7 TFLOP/s)
     }
     if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
