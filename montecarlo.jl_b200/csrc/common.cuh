@@ -103,9 +103,13 @@ struct UpdateParams {
     unsigned char* decisions;                // optional trace of accept decisions
     long long tstride;                       // per-chain stride of forced / probs / decisions
     int kb;                                  // delay block size
+    // update2.cu only: full-length delayed factors of the current block, n x kb per matrix (leading dimension ldf)
+    double* Ufac; double* Wfac; long long strideF; int ldf;
 };
 cudaError_t launch_update(const UpdateParams& p, cudaStream_t st);
 int update_pick_kb(int n, int nb);
+cudaError_t launch_update2(const UpdateParams& p, cudaStream_t st);   // block-restricted proposals + GEMM flush
+int update2_pick_kb(int n, int nb);
 
 // ---- small elementwise helpers ---------------------------------------------
 cudaError_t launch_set_identity(double* A, int n, int ld, long long stride, int batch, cudaStream_t st);

@@ -141,11 +141,29 @@ gemm_kernel(const GemmParams p)
     const int KTr = (p.K + BK - 1) / BK;
     const int KT = KTr * (p.krep > 0 ? p.krep : 1);   // krep > 1: timing experiment only (repeats the k loop)
 
+    // C read-modify-write without scalings (the rank-k flush of update2.cu, the panel updates of rdivp.cu):
+    // the accumulators start from beta / alpha * C, so the loads of C overlap the main loop instead of sitting
+    // behind it in the epilogue.  Exact for alpha = +-1.
+    const bool preload = (p.beta != 0.0) && !has_rs && !has_cs && !p.add_diag && (p.alpha == 1.0 || p.alpha == -1.0);
     double acc[MI][NJ][2];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    if (preload) {
+        const double f = p.beta * p.alpha;               // beta / alpha for alpha = +-1
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int row = m0 + wm0 + i * 8 + g;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = n0 + wn0 + j * 8 + 2 * t + e;
+                    if (row < p.M && col < p.N) acc[i][j][e] = f * C[row + (long long)col * p.ldc];
+                }
+        }
+    }
 
     TileLoader<BM, AK, NT, BK> la;
     TileLoader<BN, BKM, NT, BK> lb;
@@ -219,7 +237,7 @@ gemm_kernel(const GemmParams p)
                 if (has_cs) v *= scale_at(p.cs, mat, col);
                 if (p.add_diag && row == col) v += p.add_diag[(long long)mat * p.add_stride + row];
                 double* dst = C + row + (long long)col * p.ldc;
-                if (p.beta != 0.0) v += p.beta * (*dst);
+                if (p.beta != 0.0 && !preload) v += p.beta * (*dst);
                 *dst = v;
             }
         }
