@@ -110,6 +110,8 @@ cudaError_t launch_update(const UpdateParams& p, cudaStream_t st);
 int update_pick_kb(int n, int nb);
 cudaError_t launch_update2(const UpdateParams& p, cudaStream_t st);   // block-restricted proposals + GEMM flush
 int update2_pick_kb(int n, int nb);
+cudaError_t launch_update3(const UpdateParams& p, cudaStream_t st);   // submatrix form: G0 + Bc X Br, in-kernel flush
+int update3_pick_kb(int n, int nb);
 
 // ---- small elementwise helpers ---------------------------------------------
 cudaError_t launch_set_identity(double* A, int n, int ld, long long stride, int batch, cudaStream_t st);

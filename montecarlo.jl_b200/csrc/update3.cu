@@ -1,0 +1,482 @@
+// update3.cu -- sweep_spatial in "submatrix" form: block-restricted proposals, G0 + Bc X Br flush.
+//
+// Same mathematics and decisions as update.cu / the reference (`sweep_spatial`, local_updates.jl:23-60;
+// `propose_local` / `calculate_detratio!`, fields.jl:388-393, 440-449, 63-84; `accept_local!` ->
+// `update_greens!`, fields.jl:340-344, 271-286).  One CTA per Markov chain, the sites in blocks I of kb:
+//
+//   1. serial phase   Only G[I, I] (per flavor) is touched, and it lives in REGISTERS (one 4 x 4 patch per
+//      thread).  All lanes of warp 0 evaluate the next 32 proposals at once against the current diagonal; up
+//      to the first accepted one these are exactly the sequential decisions (a rejected proposal changes
+//      nothing).  An accepted flip applies the reference's rank-1 update to the kb x kb patches and records
+//      the block-restricted column / row of its factors.
+//   2. X              After the block, all k accepted flips together are  G' = G0 + Bc X Br  with
+//      Bc = G0[:, I] - E_I, Br = G0[I, :] and a kb x kb matrix X = MU MW that follows from the recorded
+//      restrictions alone (two triangular recurrences on k x k unit matrices: k^3 flops, no n in sight).
+//   3. flush          Per flavor: the accepted columns of G0 (Bc) and the row panel G0[I, :] are staged in
+//      shared memory with cp.async, T = X Br is formed in place (one thread per column), and G += Bc T
+//      streams over G with DMMA from shared memory at HBM rate (the flush of update.cu).
+//
+// The serial part no longer scales with n, and shared memory holds the factors of ONE flavor at a time, so
+// kb = 44 instead of 24 at n = 256 with two flavors: 6 instead of 11 read-modify-write passes over G.
+#include "common.cuh"
+#include "../../include/dqmc_rng.h"
+#include <math.h>
+#include <stdlib.h>
+#include <algorithm>
+
+namespace dqmc {
+
+constexpr int U3_KBT = 48;              // compile-time bound of kb (unrolled accept loops)
+constexpr int U3_RP = U3_KBT + 2;       // row stride of the kb x kb work matrices
+
+__device__ __forceinline__ void dmma884v(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void u3_cp_async8(void* smem, const void* gmem)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(a), "l"(gmem));
+}
+__device__ __forceinline__ void u3_cp_async16(void* smem, const void* gmem)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(a), "l"(gmem));
+}
+__device__ __forceinline__ void u3_cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+}
+__device__ __forceinline__ double u3_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+static inline int update3_ldu(int n) { return n + (((4 - n) % 16) + 16) % 16; }   // == 4 mod 16
+
+struct Upd3Shared {
+    int k, next, acc_site;
+    double coef[2];
+    int xs[U3_KBT];
+    double coefs[2][U3_KBT];
+};
+
+// Row `r` of the k x k matrix M with M[:, a] = e_a + sum_{a' < a} M[:, a'] S[a'][a] (times coefs[a] if COEF):
+// the triangular recurrences behind U = Bc_acc MU and W = MW Br_acc.  One thread, its row in registers.
+template <bool COEF>
+__device__ __forceinline__ void tri_row(int r, int k, const double* __restrict__ S, const double* __restrict__ coefs,
+                                        double* __restrict__ out)
+{
+    double hist[U3_KBT];
+#pragma unroll
+    for (int t = 0; t < U3_KBT / 8; ++t) {
+        const int a0 = 8 * t;
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = (a0 + q == r) ? 1.0 : 0.0;
+        if (a0 < k) {
+#pragma unroll
+            for (int ap = 0; ap < a0; ++ap) {
+                const double h = hist[ap];
+                const double2* s2 = reinterpret_cast<const double2*>(S + (size_t)ap * U3_RP + a0);
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2) {
+                    const double2 sv = s2[q2];
+                    acc[2 * q2] = fma(h, sv.x, acc[2 * q2]);
+                    acc[2 * q2 + 1] = fma(h, sv.y, acc[2 * q2 + 1]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                for (int qp = 0; qp < q; ++qp) acc[q] = fma(acc[qp], S[(size_t)(a0 + qp) * U3_RP + a0 + q], acc[q]);
+                if (a0 + q >= k) acc[q] = 0.0;              // (also keeps uninitialised S entries out)
+                else if (COEF) acc[q] *= coefs[a0 + q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            hist[a0 + q] = acc[q];
+            out[a0 + q] = acc[q];
+        }
+    }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256)
+update3_kernel(const UpdateParams p, const int ldu, const double em2a, const double ep2a)
+{
+    extern __shared__ __align__(16) double sm[];
+    constexpr int nb = NB, RP = U3_RP;
+    const int n = p.n, kb = p.kb, ld = p.ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
+    const int chain = blockIdx.x;
+
+    // ---- shared memory -----------------------------------------------------------------------------------
+    const size_t RS = max((size_t)kb * ldu, (size_t)2 * nb * kb * RP);   // a panel or the work matrices aliasing it
+    double* P1 = sm;                                        // [kb][ldu]  Bc_acc: accepted columns of G0 (minus e)
+    double* P2 = P1 + RS;                                   // [kb][ldu]  row panel G0[I, :] -> T = X Br
+    double* XR = P2 + RS;                                   // [nb][kb][RP]  X restricted to accepted rows: Xr[a][x]
+    double* colv = XR + (size_t)nb * kb * RP;               // [nb][kb]
+    double* rowv = colv + nb * kb;
+    double* gdiag = rowv + nb * kb;                         // [nb][kb]
+    double* sunif = gdiag + nb * kb;                        // [n]
+    Upd3Shared* sh = (Upd3Shared*)(sunif + n);
+    int8_t* sconf = (int8_t*)(sh + 1);                      // [n]
+    // work matrices of the serial phase / X build alias the panels (each nb * kb * RP doubles)
+    double* Ub = P1;                                        // [nb][kb (site x)][RP (accept a)]; later MU
+    double* Wb = P1 + (size_t)nb * kb * RP;                 // [nb][kb (accept a)][RP (site y)]; later MWt
+    double* SU = P2;                                        // [nb][kb][RP]
+    double* SWt = P2 + (size_t)nb * kb * RP;
+
+    double* G = p.G + (long long)chain * nb * p.strideG;
+    int8_t* conf = p.conf_slice + (long long)chain * p.cstride;
+    const double* utab = p.uniforms ? p.uniforms + (long long)chain * p.ustride : nullptr;
+    const unsigned char* forced = p.forced ? p.forced + (long long)chain * p.tstride : nullptr;
+
+    for (int i = tid; i < n; i += NT) {
+        sconf[i] = conf[i];
+        sunif[i] = utab ? utab[i]
+                        : dqmc_uniform(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)p.sweep, (uint32_t)p.step, (uint32_t)i);
+    }
+
+    int accepted = 0;
+    double neg_cnt = 0.0, neg_sum = 0.0, neg_min = INFINITY, neg_max = -INFINITY;   // per lane of warp 0
+
+    // register patches of G[I, I]: thread -> (flavor ob, patch (pbx, pby)) of 4 x 4 entries
+    const int NPB = (kb + 3) >> 2;
+    const bool owner = tid < nb * NPB * NPB;
+    const int ob = tid / (NPB * NPB), ot = tid % (NPB * NPB);
+    const int oxb = (ot % NPB) * 4, oyb = (ot / NPB) * 4;
+
+    for (int i0 = 0; i0 < n; i0 += kb) {
+        const int kbc = (n - i0 < kb) ? (n - i0) : kb;
+        __syncthreads();                                    // previous flush (global G), sconf / sunif visible
+        // ---- load G[I, I] into registers, its diagonal into shared memory ---------------------------------
+        double g[4][4];
+#pragma unroll
+        for (int iy = 0; iy < 4; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < 4; ++ix) {
+                const int x = oxb + ix, y = oyb + iy;
+                g[ix][iy] = (owner && x < kbc && y < kbc) ? G[(long long)ob * p.strideG + (i0 + x) + (long long)(i0 + y) * ld] : 0.0;
+            }
+        for (int e = tid; e < nb * kb; e += NT) {
+            const int b = e / kb, x = e - b * kb;
+            gdiag[e] = (x < kbc) ? G[(long long)b * p.strideG + (i0 + x) + (long long)(i0 + x) * ld] : 0.0;
+            colv[e] = 0.0; rowv[e] = 0.0;
+        }
+        if (tid == 0) { sh->k = 0; sh->next = 0; sh->acc_site = -1; }
+        __syncthreads();
+
+        // ---- serial phase --------------------------------------------------------------------------------
+        for (;;) {
+            if (warp == 0) {
+                int found = -1;
+                for (int base = sh->next; base < kbc && found < 0; base += 32) {
+                    const int j = base + lane;
+                    int acc = 0;
+                    double prob = 0.0, Rv[2] = {1.0, 1.0}, Dl[2] = {0.0, 0.0};
+                    if (j < kbc) {
+                        const double x = (double)sconf[i0 + j];
+                        const double e_dE = (x > 0.0) ? em2a : ep2a;        // exp(dE), dE = -2 alpha x
+                        const double e_mdE = (x > 0.0) ? ep2a : em2a;
+#pragma unroll
+                        for (int b = 0; b < nb; ++b) {
+                            const double gii = gdiag[b * kb + j];
+                            Dl[b] = ((p.kind == 1 && b == 1) ? e_mdE : e_dE) - 1.0;
+                            Rv[b] = 1.0 + Dl[b] * (1.0 - gii);
+                        }
+                        if (p.kind == 0) prob = e_mdE * ((nb == 1) ? Rv[0] * Rv[0] : Rv[0] * Rv[1]);
+                        else prob = Rv[0] * Rv[1];
+                        if (forced) acc = forced[i0 + j] != 0;
+                        else if (prob > 1.0) acc = 1;
+                        else acc = sunif[i0 + j] < prob;
+                    }
+                    const unsigned ballot = __ballot_sync(0xffffffffu, acc);
+                    const int first = ballot ? (__ffs(ballot) - 1) : 32;      // lanes <= first are real decisions
+                    if (j < kbc && lane <= first) {
+                        if (p.check_sign && prob < 0.0) {
+                            neg_cnt += 1.0; neg_sum += log10(fabs(prob));
+                            neg_min = fmin(neg_min, prob); neg_max = fmax(neg_max, prob);
+                        }
+                        if (p.probs) p.probs[(long long)chain * p.tstride + i0 + j] = prob;
+                        if (p.decisions) p.decisions[(long long)chain * p.tstride + i0 + j] = (unsigned char)acc;
+                    }
+                    if (first < 32) {
+                        found = base + first;
+                        if (lane == first) {
+                            const double c0 = Dl[0] * u3_rcp(Rv[0]);          // Delta / R (vldiv22!, fields.jl:176-216)
+                            const double c1 = Dl[nb - 1] * u3_rcp(Rv[nb - 1]);
+                            sconf[i0 + j] = (int8_t)(-sconf[i0 + j]); conf[i0 + j] = sconf[i0 + j];
+                            const int a = sh->k;
+                            sh->acc_site = found; sh->coef[0] = c0; sh->coef[1] = c1; sh->next = found + 1;
+                            sh->xs[a] = found; sh->coefs[0][a] = c0; sh->coefs[1][a] = c1;
+                        }
+                    }
+                }
+                if (found < 0 && lane == 0) { sh->acc_site = -1; sh->next = kbc; }
+            }
+            __syncthreads();
+            const int j = sh->acc_site;
+            if (j < 0) break;
+            const int a = sh->k;
+            if (owner) {
+                if (j >= oyb && j < oyb + 4) {              // this patch holds part of column j
+#pragma unroll
+                    for (int ix = 0; ix < 4; ++ix) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int iy = 0; iy < 4; ++iy) v = (oyb + iy == j) ? g[ix][iy] : v;
+                        const int x = oxb + ix;
+                        if (x < kb) {
+                            const double cv = v - ((x == j) ? 1.0 : 0.0);
+                            colv[ob * kb + x] = cv;
+                            Ub[((size_t)ob * kb + x) * RP + a] = cv;
+                        }
+                    }
+                }
+                if (j >= oxb && j < oxb + 4) {              // ... part of row j
+#pragma unroll
+                    for (int iy = 0; iy < 4; ++iy) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int ix = 0; ix < 4; ++ix) v = (oxb + ix == j) ? g[ix][iy] : v;
+                        const int y = oyb + iy;
+                        if (y < kb) {
+                            const double rv = sh->coef[ob] * v;
+                            rowv[ob * kb + y] = rv;
+                            Wb[((size_t)ob * kb + a) * RP + y] = rv;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (owner) {
+                double cv[4], rv[4];
+#pragma unroll
+                for (int ix = 0; ix < 4; ++ix) cv[ix] = (oxb + ix < kb) ? colv[ob * kb + oxb + ix] : 0.0;
+#pragma unroll
+                for (int iy = 0; iy < 4; ++iy) rv[iy] = (oyb + iy < kb) ? rowv[ob * kb + oyb + iy] : 0.0;
+#pragma unroll
+                for (int iy = 0; iy < 4; ++iy)
+#pragma unroll
+                    for (int ix = 0; ix < 4; ++ix) g[ix][iy] = fma(cv[ix], rv[iy], g[ix][iy]);
+            }
+            if (warp == 0) {                                // the diagonal the next decisions read
+                for (int e = lane; e < nb * kb; e += 32) gdiag[e] = fma(colv[e], rowv[e], gdiag[e]);
+                if (lane == 0) sh->k = a + 1;
+                __syncwarp();
+            }
+        }
+        const int k = sh->k;
+        accepted += k;
+        __syncthreads();
+        if (k == 0) continue;                               // uniform over the CTA: nothing to flush
+
+        // ---- X = MU MW restricted to the accepted sites ---------------------------------------------------------
+        // SU[a'][a] = Wb[a'][x_a], SWt[a'][a] = Ub[x_a][a']
+        for (int e = tid; e < nb * k * U3_KBT; e += NT) {
+            const int b = e / (k * U3_KBT), r = e - b * (k * U3_KBT);
+            const int a = r % U3_KBT, ap = r / U3_KBT;
+            if (a < k) {
+                const int xa = sh->xs[a];
+                SU[((size_t)b * kb + ap) * RP + a] = Wb[((size_t)b * kb + ap) * RP + xa];
+                SWt[((size_t)b * kb + ap) * RP + a] = Ub[((size_t)b * kb + xa) * RP + ap];
+            }
+        }
+        __syncthreads();
+        {
+            // group 0 .. nb-1: rows of MU (over Ub), group nb .. 2nb-1: rows of MWt (over Wb)
+            const int grp = tid / U3_KBT, r = tid - grp * U3_KBT;
+            if (grp < 2 * nb && r < k) {
+                const int b = grp % nb;
+                if (grp < nb) tri_row<false>(r, k, SU + (size_t)b * kb * RP, sh->coefs[b], Ub + ((size_t)b * kb + r) * RP);
+                else tri_row<true>(r, k, SWt + (size_t)b * kb * RP, sh->coefs[b], Wb + ((size_t)b * kb + r) * RP);
+            }
+        }
+        __syncthreads();
+        // Xr[b][a1][x_{a2}] = sum_a MU[a1][a] MWt[a2][a]; zero on non-accepted columns
+        for (int e = tid; e < nb * kb * RP; e += NT) XR[e] = 0.0;
+        __syncthreads();
+        for (int e = tid; e < nb * k * k; e += NT) {
+            const int b = e / (k * k), r = e - b * k * k;
+            const int a2 = r % k, a1 = r / k;
+            const double* mu = Ub + ((size_t)b * kb + a1) * RP;
+            const double* mw = Wb + ((size_t)b * kb + a2) * RP;
+            double s = 0.0;
+            for (int a = (a1 > a2 ? a1 : a2); a < k; ++a) s = fma(mu[a], mw[a], s);
+            XR[((size_t)b * kb + a1) * RP + sh->xs[a2]] = s;
+        }
+        __syncthreads();
+
+        // ---- flush, one flavor at a time: G_b += Bc_acc (Xr Br) -----------------------------------------------------
+        const int g8 = lane >> 2, t4 = lane & 3;
+        const int tiles = (n + 31) / 32;
+        const int k4 = (k + 3) / 4;
+        for (int b = 0; b < nb; ++b) {
+            double* Gb = G + (long long)b * p.strideG;
+            // accepted columns of G0 -> P1[a][r]; row panel G0[I, :] -> P2[x][c]
+            for (int a = warp; a < k; a += nwarps) {
+                const double* src = Gb + (long long)(i0 + sh->xs[a]) * ld;
+                for (int r2 = lane * 2; r2 < n; r2 += 64) {
+                    if (r2 + 1 < n) u3_cp_async16(P1 + (size_t)a * ldu + r2, src + r2);
+                    else u3_cp_async8(P1 + (size_t)a * ldu + r2, src + r2);
+                }
+            }
+            for (int c = warp; c < n; c += nwarps)
+                for (int x = lane; x < kbc; x += 32) u3_cp_async8(P2 + (size_t)x * ldu + c, Gb + (i0 + x) + (long long)c * ld);
+            u3_cp_async_wait_all();
+            __syncthreads();
+            if (tid < k) P1[(size_t)tid * ldu + i0 + sh->xs[tid]] -= 1.0;       // Bc = G0[:, I] - E_I
+            // T = Xr Br in place: one thread per column
+            const double* xr = XR + (size_t)b * kb * RP;
+            for (int c = tid; c < n; c += NT) {
+                double br[U3_KBT];
+#pragma unroll
+                for (int x = 0; x < U3_KBT; ++x) br[x] = (x < kbc) ? P2[(size_t)x * ldu + c] : 0.0;
+                for (int a = 0; a < k; ++a) {
+                    const double2* x2 = reinterpret_cast<const double2*>(xr + (size_t)a * RP);
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int x = 0; x < U3_KBT / 2; ++x) {
+                        const double2 xv = x2[x];
+                        s0 = fma(xv.x, br[2 * x], s0);
+                        s1 = fma(xv.y, br[2 * x + 1], s1);
+                    }
+                    P2[(size_t)a * ldu + c] = s0 + s1;
+                }
+            }
+            __syncthreads();
+            // G_b += sum_{a < k} P1[a][:] P2[a][:]^T, 32 x 32 tiles per warp with a one-tile look-ahead
+            {
+                const int ntl = tiles * tiles;
+                auto load_tile = [&](int tl, double (&dst)[4][4][2]) {
+                    const int tm = (tl % tiles) * 32, tn = (tl / tiles) * 32;
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const int r = tm + mi * 8 + g8;
+#pragma unroll
+                        for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = tn + nj * 8 + 2 * t4 + e;
+                                dst[mi][nj][e] = (r < n && c < n) ? Gb[r + (long long)c * ld] : 0.0;
+                            }
+                    }
+                };
+                double cur[4][4][2], nxt[4][4][2];
+                if (warp < ntl) load_tile(warp, cur);
+                for (int tl = warp; tl < ntl; tl += nwarps) {
+                    if (tl + nwarps < ntl) load_tile(tl + nwarps, nxt);
+                    const int tm = (tl % tiles) * 32, tn = (tl / tiles) * 32;
+                    for (int kk = 0; kk < k4; ++kk) {
+                        const int a = kk * 4 + t4;
+                        const bool live = a < k;
+                        double af[4], bf[4];
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi) {
+                            const int r = tm + mi * 8 + g8;
+                            af[mi] = (live && r < n) ? P1[(size_t)a * ldu + r] : 0.0;
+                        }
+#pragma unroll
+                        for (int nj = 0; nj < 4; ++nj) {
+                            const int c = tn + nj * 8 + g8;
+                            bf[nj] = (live && c < n) ? P2[(size_t)a * ldu + c] : 0.0;
+                        }
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                            for (int nj = 0; nj < 4; ++nj) dmma884v(cur[mi][nj][0], cur[mi][nj][1], af[mi], bf[nj]);
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const int r = tm + mi * 8 + g8;
+#pragma unroll
+                        for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = tn + nj * 8 + 2 * t4 + e;
+                                if (r < n && c < n) Gb[r + (long long)c * ld] = cur[mi][nj][e];
+                                cur[mi][nj][e] = nxt[mi][nj][e];
+                            }
+                    }
+                }
+            }
+            __syncthreads();                                // P1 / P2 are restaged for the next flavor / block
+        }
+    }
+
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            neg_cnt += __shfl_xor_sync(0xffffffffu, neg_cnt, o); neg_sum += __shfl_xor_sync(0xffffffffu, neg_sum, o);
+            neg_min = fmin(neg_min, __shfl_xor_sync(0xffffffffu, neg_min, o));
+            neg_max = fmax(neg_max, __shfl_xor_sync(0xffffffffu, neg_max, o));
+        }
+    }
+    if (tid == 0) {
+        if (p.accepted) p.accepted[chain] += accepted;
+        if (p.stats && neg_cnt > 0.0) {
+            double* s = p.stats + (long long)chain * 4;
+            s[0] += neg_cnt; s[1] += neg_sum; s[2] = fmin(s[2], neg_min); s[3] = fmax(s[3], neg_max);
+        }
+    }
+}
+
+static size_t update3_smem(int n, int nb, int kb)
+{
+    const int ldu = update3_ldu(n);
+    const size_t rs = std::max((size_t)kb * ldu, (size_t)2 * nb * kb * U3_RP);
+    return (2 * rs + (size_t)nb * kb * U3_RP + 3 * nb * kb + n) * sizeof(double) + sizeof(Upd3Shared) + n + 16;
+}
+
+int update3_pick_kb(int n, int nb)
+{
+    // constraints: kb <= 48 (unrolled accept loops); (kb / 4)^2 * nb register patches <= 256 threads; 227 KB
+    int best = 4;
+    for (int kb = 4; kb <= U3_KBT; kb += 4) {
+        const int npb = kb / 4;
+        if (npb * npb * nb > 256) break;
+        if (update3_smem(n, nb, kb) > 225 * 1024) break;
+        best = kb;
+    }
+    // no point in a block larger than the lattice; prefer the smallest kb with the same number of passes
+    const int nn = (n + 3) & ~3;
+    if (best > nn) best = nn;
+    const int passes = (n + best - 1) / best;
+    while (best > 4 && (n + (best - 4) - 1) / (best - 4) == passes) best -= 4;
+    return best;
+}
+
+cudaError_t launch_update3(const UpdateParams& p, cudaStream_t st)
+{
+    if (p.n_chains <= 0) return cudaSuccess;
+    if (p.kb < 4 || p.kb > U3_KBT || (p.kb & 3) || p.nb < 1 || p.nb > 2) return cudaErrorInvalidValue;
+    const int ldu = update3_ldu(p.n);
+    const size_t smem = update3_smem(p.n, p.nb, p.kb);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    const double em2a = exp(-2.0 * p.alpha), ep2a = exp(2.0 * p.alpha);
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[p.nb - 1]) {
+        cudaError_t e = (p.nb == 1)
+            ? cudaFuncSetAttribute(update3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+            : cudaFuncSetAttribute(update3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[p.nb - 1] = smem;
+    }
+    if (p.nb == 1) update3_kernel<1><<<(unsigned)p.n_chains, 256, smem, st>>>(p, ldu, em2a, ep2a);
+    else update3_kernel<2><<<(unsigned)p.n_chains, 256, smem, st>>>(p, ldu, em2a, ep2a);
+    ++g_kernel_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace dqmc
