@@ -125,10 +125,9 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
     double* P1 = sm;                                        // [kb][ldu]  Bc_acc: accepted columns of G0 (minus e)
     double* P2 = P1 + RS;                                   // [kb][ldu]  row panel G0[I, :] -> T = X Br
     double* XR = P2 + RS;                                   // [nb][kb][RP]  X restricted to accepted rows: Xr[a][x]
-    double* colv = XR + (size_t)nb * kb * RP;               // [nb][kb]
-    double* rowv = colv + nb * kb;
-    double* gdiag = rowv + nb * kb;                         // [nb][kb]
-    double* sunif = gdiag + nb * kb;                        // [n]
+    double* colv = XR + (size_t)nb * kb * RP;
+    double* rowv = colv + 2 * nb * kb;                      // colv, rowv: [2 (parity of the accept)][nb][kb]
+    double* sunif = rowv + 2 * nb * kb;                     // [n]
     Upd3Shared* sh = (Upd3Shared*)(sunif + n);
     int8_t* sconf = (int8_t*)(sh + 1);                      // [n]
     // work matrices of the serial phase / X build alias the panels (each nb * kb * RP doubles)
@@ -169,66 +168,80 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
                 const int x = oxb + ix, y = oyb + iy;
                 g[ix][iy] = (owner && x < kbc && y < kbc) ? G[(long long)ob * p.strideG + (i0 + x) + (long long)(i0 + y) * ld] : 0.0;
             }
-        for (int e = tid; e < nb * kb; e += NT) {
-            const int b = e / kb, x = e - b * kb;
-            gdiag[e] = (x < kbc) ? G[(long long)b * p.strideG + (i0 + x) + (long long)(i0 + x) * ld] : 0.0;
-            colv[e] = 0.0; rowv[e] = 0.0;
+        // Every lane of EVERY warp tracks the diagonal entries of the sites lane and lane + 32 in registers and takes
+        // the decisions redundantly: (site, Delta / R) of an accepted flip are known to all threads without a
+        // broadcast, so an accept costs one CTA barrier (between the extraction of its restricted column / row and
+        // their use; colv / rowv are double buffered).
+        double gd[2][2], Dl[2][2], emd[2], un[2];
+        int fc[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = lane + 32 * h;
+            const bool in = j < kbc;
+            const double x = in ? (double)sconf[i0 + j] : 1.0;
+            const double e_dE = (x > 0.0) ? em2a : ep2a;               // exp(dE), dE = -2 alpha x
+            const double e_mdE = (x > 0.0) ? ep2a : em2a;
+            emd[h] = e_mdE;
+            un[h] = in ? sunif[i0 + j] : 2.0;
+            fc[h] = (in && forced) ? (int)forced[i0 + j] : -1;
+#pragma unroll
+            for (int b = 0; b < nb; ++b) {
+                gd[b][h] = in ? G[(long long)b * p.strideG + (i0 + j) + (long long)(i0 + j) * ld] : 0.0;
+                Dl[b][h] = ((p.kind == 1 && b == 1) ? e_mdE : e_dE) - 1.0;
+            }
         }
-        if (tid == 0) { sh->k = 0; sh->next = 0; sh->acc_site = -1; }
-        __syncthreads();
+        __syncthreads();                                    // panels of the previous block are no longer read
 
         // ---- serial phase --------------------------------------------------------------------------------
+        int k = 0, next = 0;
         for (;;) {
-            if (warp == 0) {
-                int found = -1;
-                for (int base = sh->next; base < kbc && found < 0; base += 32) {
-                    const int j = base + lane;
-                    int acc = 0;
-                    double prob = 0.0, Rv[2] = {1.0, 1.0}, Dl[2] = {0.0, 0.0};
-                    if (j < kbc) {
-                        const double x = (double)sconf[i0 + j];
-                        const double e_dE = (x > 0.0) ? em2a : ep2a;        // exp(dE), dE = -2 alpha x
-                        const double e_mdE = (x > 0.0) ? ep2a : em2a;
+            double prob[2], cf[2][2];
+            int acc[2];
 #pragma unroll
-                        for (int b = 0; b < nb; ++b) {
-                            const double gii = gdiag[b * kb + j];
-                            Dl[b] = ((p.kind == 1 && b == 1) ? e_mdE : e_dE) - 1.0;
-                            Rv[b] = 1.0 + Dl[b] * (1.0 - gii);
+            for (int h = 0; h < 2; ++h) {
+                const int j = lane + 32 * h;
+                const bool elig = (j >= next) && (j < kbc);
+                double Rv[2];
+#pragma unroll
+                for (int b = 0; b < nb; ++b) {
+                    Rv[b] = fma(Dl[b][h], 1.0 - gd[b][h], 1.0);
+                    cf[b][h] = Dl[b][h] * u3_rcp(Rv[b]);               // Delta / R (vldiv22!), speculative
+                }
+                if (nb == 1) cf[1][h] = cf[0][h];
+                if (p.kind == 0) prob[h] = emd[h] * ((nb == 1) ? Rv[0] * Rv[0] : Rv[0] * Rv[1]);
+                else prob[h] = Rv[0] * Rv[1];
+                int a_ = (fc[h] >= 0) ? (fc[h] != 0) : ((prob[h] > 1.0) ? 1 : (un[h] < prob[h]));
+                acc[h] = elig ? a_ : 0;
+            }
+            const unsigned b0 = __ballot_sync(0xffffffffu, acc[0]);
+            const unsigned b1 = __ballot_sync(0xffffffffu, acc[1]);
+            const int jacc = b0 ? (__ffs(b0) - 1) : (b1 ? 32 + __ffs(b1) - 1 : -1);
+            if (warp == 0) {                                // traces and statistics of the real decisions
+                const int jlast = (jacc >= 0) ? jacc : kbc - 1;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = lane + 32 * h;
+                    if (j >= next && j <= jlast) {
+                        if (p.check_sign && prob[h] < 0.0) {
+                            neg_cnt += 1.0; neg_sum += log10(fabs(prob[h]));
+                            neg_min = fmin(neg_min, prob[h]); neg_max = fmax(neg_max, prob[h]);
                         }
-                        if (p.kind == 0) prob = e_mdE * ((nb == 1) ? Rv[0] * Rv[0] : Rv[0] * Rv[1]);
-                        else prob = Rv[0] * Rv[1];
-                        if (forced) acc = forced[i0 + j] != 0;
-                        else if (prob > 1.0) acc = 1;
-                        else acc = sunif[i0 + j] < prob;
-                    }
-                    const unsigned ballot = __ballot_sync(0xffffffffu, acc);
-                    const int first = ballot ? (__ffs(ballot) - 1) : 32;      // lanes <= first are real decisions
-                    if (j < kbc && lane <= first) {
-                        if (p.check_sign && prob < 0.0) {
-                            neg_cnt += 1.0; neg_sum += log10(fabs(prob));
-                            neg_min = fmin(neg_min, prob); neg_max = fmax(neg_max, prob);
-                        }
-                        if (p.probs) p.probs[(long long)chain * p.tstride + i0 + j] = prob;
-                        if (p.decisions) p.decisions[(long long)chain * p.tstride + i0 + j] = (unsigned char)acc;
-                    }
-                    if (first < 32) {
-                        found = base + first;
-                        if (lane == first) {
-                            const double c0 = Dl[0] * u3_rcp(Rv[0]);          // Delta / R (vldiv22!, fields.jl:176-216)
-                            const double c1 = Dl[nb - 1] * u3_rcp(Rv[nb - 1]);
-                            sconf[i0 + j] = (int8_t)(-sconf[i0 + j]); conf[i0 + j] = sconf[i0 + j];
-                            const int a = sh->k;
-                            sh->acc_site = found; sh->coef[0] = c0; sh->coef[1] = c1; sh->next = found + 1;
-                            sh->xs[a] = found; sh->coefs[0][a] = c0; sh->coefs[1][a] = c1;
-                        }
+                        if (p.probs) p.probs[(long long)chain * p.tstride + i0 + j] = prob[h];
+                        if (p.decisions) p.decisions[(long long)chain * p.tstride + i0 + j] = (unsigned char)(j == jacc);
                     }
                 }
-                if (found < 0 && lane == 0) { sh->acc_site = -1; sh->next = kbc; }
             }
-            __syncthreads();
-            const int j = sh->acc_site;
-            if (j < 0) break;
-            const int a = sh->k;
+            if (jacc < 0) break;
+            const int src = jacc & 31, hh = jacc >> 5;
+            const double c0 = __shfl_sync(0xffffffffu, hh ? cf[0][1] : cf[0][0], src);
+            const double c1 = __shfl_sync(0xffffffffu, hh ? cf[1][1] : cf[1][0], src);
+            const int a = k, j = jacc;
+            if (warp == 0 && lane == src) {
+                sconf[i0 + j] = (int8_t)(-sconf[i0 + j]); conf[i0 + j] = sconf[i0 + j];
+                sh->xs[a] = j; sh->coefs[0][a] = c0; sh->coefs[1][a] = c1;
+            }
+            double* cvb = colv + (a & 1) * nb * kb;
+            double* rvb = rowv + (a & 1) * nb * kb;
             if (owner) {
                 if (j >= oyb && j < oyb + 4) {              // this patch holds part of column j
 #pragma unroll
@@ -237,25 +250,22 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
 #pragma unroll
                         for (int iy = 0; iy < 4; ++iy) v = (oyb + iy == j) ? g[ix][iy] : v;
                         const int x = oxb + ix;
-                        if (x < kb) {
-                            const double cv = v - ((x == j) ? 1.0 : 0.0);
-                            colv[ob * kb + x] = cv;
-                            Ub[((size_t)ob * kb + x) * RP + a] = cv;
-                        }
+                        const double cv = v - ((x == j) ? 1.0 : 0.0);
+                        cvb[ob * kb + x] = cv;
+                        Ub[((size_t)ob * kb + x) * RP + a] = cv;
                     }
                 }
                 if (j >= oxb && j < oxb + 4) {              // ... part of row j
+                    const double cc = ob ? c1 : c0;
 #pragma unroll
                     for (int iy = 0; iy < 4; ++iy) {
                         double v = 0.0;
 #pragma unroll
                         for (int ix = 0; ix < 4; ++ix) v = (oxb + ix == j) ? g[ix][iy] : v;
                         const int y = oyb + iy;
-                        if (y < kb) {
-                            const double rv = sh->coef[ob] * v;
-                            rowv[ob * kb + y] = rv;
-                            Wb[((size_t)ob * kb + a) * RP + y] = rv;
-                        }
+                        const double rv = cc * v;
+                        rvb[ob * kb + y] = rv;
+                        Wb[((size_t)ob * kb + a) * RP + y] = rv;
                     }
                 }
             }
@@ -263,21 +273,25 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
             if (owner) {
                 double cv[4], rv[4];
 #pragma unroll
-                for (int ix = 0; ix < 4; ++ix) cv[ix] = (oxb + ix < kb) ? colv[ob * kb + oxb + ix] : 0.0;
+                for (int ix = 0; ix < 4; ++ix) cv[ix] = cvb[ob * kb + oxb + ix];
 #pragma unroll
-                for (int iy = 0; iy < 4; ++iy) rv[iy] = (oyb + iy < kb) ? rowv[ob * kb + oyb + iy] : 0.0;
+                for (int iy = 0; iy < 4; ++iy) rv[iy] = rvb[ob * kb + oyb + iy];
 #pragma unroll
                 for (int iy = 0; iy < 4; ++iy)
 #pragma unroll
                     for (int ix = 0; ix < 4; ++ix) g[ix][iy] = fma(cv[ix], rv[iy], g[ix][iy]);
             }
-            if (warp == 0) {                                // the diagonal the next decisions read
-                for (int e = lane; e < nb * kb; e += 32) gdiag[e] = fma(colv[e], rowv[e], gdiag[e]);
-                if (lane == 0) sh->k = a + 1;
-                __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int jj = lane + 32 * h;
+                if (jj < kbc) {
+#pragma unroll
+                    for (int b = 0; b < nb; ++b) gd[b][h] = fma(cvb[b * kb + jj], rvb[b * kb + jj], gd[b][h]);
+                }
             }
+            k = a + 1; next = j + 1;
         }
-        const int k = sh->k;
+        if (tid == 0) sh->k = k;
         accepted += k;
         __syncthreads();
         if (k == 0) continue;                               // uniform over the CTA: nothing to flush
@@ -304,7 +318,7 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
             }
         }
         __syncthreads();
-        // Xr[b][a1][x_{a2}] = sum_a MU[a1][a] MWt[a2][a]; zero on non-accepted columns
+        // X_acc[b][a1][a2] = sum_a MU[a1][a] MWt[a2][a] (compact: accepted flips only), zero padded
         for (int e = tid; e < nb * kb * RP; e += NT) XR[e] = 0.0;
         __syncthreads();
         for (int e = tid; e < nb * k * k; e += NT) {
@@ -312,9 +326,14 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
             const int a2 = r % k, a1 = r / k;
             const double* mu = Ub + ((size_t)b * kb + a1) * RP;
             const double* mw = Wb + ((size_t)b * kb + a2) * RP;
-            double s = 0.0;
-            for (int a = (a1 > a2 ? a1 : a2); a < k; ++a) s = fma(mu[a], mw[a], s);
-            XR[((size_t)b * kb + a1) * RP + sh->xs[a2]] = s;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // MU[a1][a] = 0 for a < a1, MWt[a2][a] = 0 for a < a2
+            int a = (a1 > a2 ? a1 : a2);
+            for (; a + 3 < k; a += 4) {
+                s0 = fma(mu[a], mw[a], s0); s1 = fma(mu[a + 1], mw[a + 1], s1);
+                s2 = fma(mu[a + 2], mw[a + 2], s2); s3 = fma(mu[a + 3], mw[a + 3], s3);
+            }
+            for (; a < k; ++a) s0 = fma(mu[a], mw[a], s0);
+            XR[((size_t)b * kb + a1) * RP + a2] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
 
@@ -337,78 +356,106 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
             u3_cp_async_wait_all();
             __syncthreads();
             if (tid < k) P1[(size_t)tid * ldu + i0 + sh->xs[tid]] -= 1.0;       // Bc = G0[:, I] - E_I
-            // T = Xr Br in place: one thread per column
+            const int ntl = tiles * tiles;
+            const bool full = (n & 31) == 0;
+            auto tile_ptr = [&](int tl, int& tm, int& tn) -> double* {
+                tm = (tl % tiles) * 32; tn = (tl / tiles) * 32;
+                return Gb + (tm + g8) + (long long)(tn + 2 * t4) * ld;      // element (mi, nj, e) at + mi * 8 + (nj * 8 + e) * ld
+            };
+            auto load_tile = [&](int tl, double (&dst)[4][4][2]) {
+                int tm, tn;
+                const double* gp = tile_ptr(tl, tm, tn);
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double* gc = gp + (long long)(nj * 8 + e) * ld;
+                        const bool cok = full || (tn + nj * 8 + 2 * t4 + e < n);
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+                            dst[mi][nj][e] = (cok && (full || tm + mi * 8 + g8 < n)) ? gc[mi * 8] : 0.0;
+                    }
+            };
+            // the first G tile of this warp travels while T is formed (it does not depend on T)
+            double cur[4][4][2];
+            if (warp < ntl) load_tile(warp, cur);
+            // T = X_acc Br_acc in place with DMMA: a warp owns 32 columns of the panel, reads its accepted rows
+            // (gathered through xs) for all k before it writes rows 0 .. 4 k4 - 1 of the same columns.  Rows
+            // k .. 4 k4 - 1 of X are zero, so the pad rows of the panel come out as zeros.
             const double* xr = XR + (size_t)b * kb * RP;
-            for (int c = tid; c < n; c += NT) {
-                double br[U3_KBT];
+            for (int c0 = warp * 32; c0 < n; c0 += 32 * nwarps) {
+                double tacc[U3_KBT / 8][4][2];
 #pragma unroll
-                for (int x = 0; x < U3_KBT; ++x) br[x] = (x < kbc) ? P2[(size_t)x * ldu + c] : 0.0;
-                for (int a = 0; a < k; ++a) {
-                    const double2* x2 = reinterpret_cast<const double2*>(xr + (size_t)a * RP);
-                    double s0 = 0.0, s1 = 0.0;
+                for (int mi = 0; mi < U3_KBT / 8; ++mi)
 #pragma unroll
-                    for (int x = 0; x < U3_KBT / 2; ++x) {
-                        const double2 xv = x2[x];
-                        s0 = fma(xv.x, br[2 * x], s0);
-                        s1 = fma(xv.y, br[2 * x + 1], s1);
-                    }
-                    P2[(size_t)a * ldu + c] = s0 + s1;
+                    for (int nj = 0; nj < 4; ++nj) tacc[mi][nj][0] = tacc[mi][nj][1] = 0.0;
+                for (int kk = 0; kk < k4; ++kk) {
+                    const int ap = kk * 4 + t4;
+                    const int xa = (ap < k) ? sh->xs[ap] : 0;               // X column ap is zero for ap >= k
+                    double bf[4];
+#pragma unroll
+                    for (int nj = 0; nj < 4; ++nj) bf[nj] = P2[(size_t)xa * ldu + c0 + nj * 8 + g8];
+#pragma unroll
+                    for (int mi = 0; mi < U3_KBT / 8; ++mi)
+                        if (mi * 8 < 4 * k4) {              // uniform
+                            const double af = (mi * 8 + g8 < kb) ? xr[(size_t)(mi * 8 + g8) * RP + ap] : 0.0;
+#pragma unroll
+                            for (int nj = 0; nj < 4; ++nj) dmma884v(tacc[mi][nj][0], tacc[mi][nj][1], af, bf[nj]);
+                        }
                 }
-            }
-            __syncthreads();
-            // G_b += sum_{a < k} P1[a][:] P2[a][:]^T, 32 x 32 tiles per warp with a one-tile look-ahead
-            {
-                const int ntl = tiles * tiles;
-                auto load_tile = [&](int tl, double (&dst)[4][4][2]) {
-                    const int tm = (tl % tiles) * 32, tn = (tl / tiles) * 32;
+                __syncwarp();
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) {
-                        const int r = tm + mi * 8 + g8;
+                for (int mi = 0; mi < U3_KBT / 8; ++mi)
+                    if (mi * 8 < 4 * k4) {
+                        const int row = mi * 8 + g8;
+                        if (row < 4 * k4) {
 #pragma unroll
-                        for (int nj = 0; nj < 4; ++nj)
+                            for (int nj = 0; nj < 4; ++nj)
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int c = tn + nj * 8 + 2 * t4 + e;
-                                dst[mi][nj][e] = (r < n && c < n) ? Gb[r + (long long)c * ld] : 0.0;
-                            }
+                                for (int e = 0; e < 2; ++e) {
+                                    const int c = c0 + nj * 8 + 2 * t4 + e;
+                                    if (c < n) P2[(size_t)row * ldu + c] = tacc[mi][nj][e];
+                                }
+                        }
                     }
-                };
-                double cur[4][4][2], nxt[4][4][2];
-                if (warp < ntl) load_tile(warp, cur);
+            }
+            for (int e = tid; e < (4 * k4 - k) * ldu; e += NT) P1[(size_t)k * ldu + e] = 0.0;   // pad rows (P2's: per column above)
+            __syncthreads();
+            // G_b += sum_{a < k} P1[a][:] P2[a][:]^T, 32 x 32 tiles per warp with a one-tile look-ahead.  The pad rows
+            // k .. 4 k4 - 1 of both panels are zero, so the k loop needs no predicates; rows / columns >= n of an edge
+            // tile read whatever follows in shared memory and are never stored.
+            {
+                double nxt[4][4][2];
                 for (int tl = warp; tl < ntl; tl += nwarps) {
                     if (tl + nwarps < ntl) load_tile(tl + nwarps, nxt);
-                    const int tm = (tl % tiles) * 32, tn = (tl / tiles) * 32;
+                    int tm, tn;
+                    double* gp = tile_ptr(tl, tm, tn);
+                    const double* pa = P1 + (size_t)t4 * ldu + tm + g8;
+                    const double* pb = P2 + (size_t)t4 * ldu + tn + g8;
                     for (int kk = 0; kk < k4; ++kk) {
-                        const int a = kk * 4 + t4;
-                        const bool live = a < k;
                         double af[4], bf[4];
 #pragma unroll
-                        for (int mi = 0; mi < 4; ++mi) {
-                            const int r = tm + mi * 8 + g8;
-                            af[mi] = (live && r < n) ? P1[(size_t)a * ldu + r] : 0.0;
-                        }
+                        for (int mi = 0; mi < 4; ++mi) af[mi] = pa[mi * 8];
 #pragma unroll
-                        for (int nj = 0; nj < 4; ++nj) {
-                            const int c = tn + nj * 8 + g8;
-                            bf[nj] = (live && c < n) ? P2[(size_t)a * ldu + c] : 0.0;
-                        }
+                        for (int nj = 0; nj < 4; ++nj) bf[nj] = pb[nj * 8];
+                        pa += 4 * ldu; pb += 4 * ldu;
 #pragma unroll
                         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                             for (int nj = 0; nj < 4; ++nj) dmma884v(cur[mi][nj][0], cur[mi][nj][1], af[mi], bf[nj]);
                     }
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) {
-                        const int r = tm + mi * 8 + g8;
+                    for (int nj = 0; nj < 4; ++nj)
 #pragma unroll
-                        for (int nj = 0; nj < 4; ++nj)
+                        for (int e = 0; e < 2; ++e) {
+                            double* gc = gp + (long long)(nj * 8 + e) * ld;
+                            const bool cok = full || (tn + nj * 8 + 2 * t4 + e < n);
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int c = tn + nj * 8 + 2 * t4 + e;
-                                if (r < n && c < n) Gb[r + (long long)c * ld] = cur[mi][nj][e];
+                            for (int mi = 0; mi < 4; ++mi) {
+                                if (cok && (full || tm + mi * 8 + g8 < n)) gc[mi * 8] = cur[mi][nj][e];
                                 cur[mi][nj][e] = nxt[mi][nj][e];
                             }
-                    }
+                        }
                 }
             }
             __syncthreads();                                // P1 / P2 are restaged for the next flavor / block
@@ -436,7 +483,7 @@ static size_t update3_smem(int n, int nb, int kb)
 {
     const int ldu = update3_ldu(n);
     const size_t rs = std::max((size_t)kb * ldu, (size_t)2 * nb * kb * U3_RP);
-    return (2 * rs + (size_t)nb * kb * U3_RP + 3 * nb * kb + n) * sizeof(double) + sizeof(Upd3Shared) + n + 16;
+    return (2 * rs + (size_t)nb * kb * U3_RP + 4 * nb * kb + n) * sizeof(double) + sizeof(Upd3Shared) + n + 16;
 }
 
 int update3_pick_kb(int n, int nb)
