@@ -280,9 +280,15 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
     // CTA winner -> publish (norm, column index, column tail from row j) into every peer
     auto publish = [&](int j) {
         const int q = j & 1;
-        double bv = wbval[q * 32]; int bc = wbcol[q * 32];
-        for (int w = 1; w < nwarps; ++w) {
-            const double ov = wbval[q * 32 + w]; const int oc = wbcol[q * 32 + w];
+        // CTA winner: every warp reduces the <= 16 warp candidates with a shuffle butterfly (the order of the
+        // comparisons does not matter: (norm, -column) is a total order), instead of every thread scanning them
+        const int wl = lane & 15;
+        double bv = (wl < nwarps) ? wbval[q * 32 + wl] : -2.0;
+        int bc = (wl < nwarps) ? wbcol[q * 32 + wl] : 0x7fffffff;
+#pragma unroll
+        for (int o = 1; o <= 8; o <<= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
             if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
         }
         const int s = (bv >= 0.0) ? ((bc - rank) >> csh) : -1;
@@ -339,11 +345,18 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
         if (store_prev) store_v(j - 1, vprev);
         if (CS > 1) cluster_wait();
         // ---- global winner, identical in every CTA ------------------------------------------
-        double bv = candval[q * 8]; int bc = candcol[q * 8], br = 0;
-        for (int r = 1; r < CS; ++r) {
-            const double ov = candval[q * 8 + r]; const int oc = candcol[q * 8 + r];
-            if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; br = r; }
+        // cluster winner, identical in every CTA and warp: butterfly over the <= 8 CTA candidates; the owner of
+        // column c is CTA c % CS (cyclic dealing)
+        const int cl = lane & 7;
+        double bv = (cl < CS) ? candval[q * 8 + cl] : -2.0;
+        int bc = (cl < CS) ? candcol[q * 8 + cl] : 0x7fffffff;
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
         }
+        const int br = (bv >= 0.0) ? (bc & (CS - 1)) : 0;
         const double* raw = vbuf + ((size_t)q * CS + br) * nv;
         // ---- reflector (UDT.jl:157-172) ------------------------------------------------------
         double xi1 = raw[j], tau, rjj, inv;
