@@ -432,7 +432,9 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     c->ldv = ((c->N + 31) / 32) * 32;
     // update3.cu (submatrix form) is the default; update.cu (delayed rank-kb factors, kb = 24 at cfg 4) and update2.cu
     // (GEMM flush, measured slower) stay selectable for A/B runs
-    c->update_version = getenv("DQMC_UPDATE_V1") ? 1 : (getenv("DQMC_UPDATE_V2") ? 2 : 3);
+    // (measured: update3 wins from n = 144 up -- cfg 3 / 4 / 5 -- and loses at n = 64, where its per-block overheads
+    // outweigh the saved flush passes: cfg 2 5195 vs 5970 sweeps/s)
+    c->update_version = getenv("DQMC_UPDATE_V1") ? 1 : (getenv("DQMC_UPDATE_V2") ? 2 : (getenv("DQMC_UPDATE_V3") ? 3 : (c->N >= 96 ? 3 : 1)));
     if (c->update_version == 1) {
         c->kb = d->delay_block > 0 ? ((d->delay_block + 3) & ~3) : update_pick_kb(c->N, c->nb);
         const int kmax = update_pick_kb(c->N, c->nb);

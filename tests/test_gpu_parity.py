@@ -448,3 +448,30 @@ def test_check_propagation_error_off_is_identical(b200):
         acc, p, d = ctx.sweep_traced()
         out.append((d, ctx.greens()))
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+# ===================================================================== every local-update kernel variant
+@pytest.mark.parametrize("version", [1, 2, 3])
+def test_every_update_kernel_variant(b200, version, monkeypatch):
+    """The library picks update.cu (delayed rank-kb factors) below n = 96 and update3.cu (submatrix form) above;
+    update2.cu (GEMM flush) is opt-in.  All three must take the oracle's decisions on every geometry: one / two
+    flavor blocks, odd n, ragged delay blocks, single range, and n > kb (several blocks per slice)."""
+    for v in (1, 2, 3):
+        monkeypatch.delenv(f"DQMC_UPDATE_V{v}", raising=False)
+    monkeypatch.setenv(f"DQMC_UPDATE_V{version}", "1")
+    cases = [("square", (4, 4), 4.0, 1.0, 3, 10, 0), ("square", (6, 6), -4.0, 1.0, 2, 5, 0),
+             ("square", (7, 7), -3.0, 1.3, 2, 10, 12), ("honeycomb", (3, 3), 2.0, 0.7, 1, 3, 4),
+             ("square", (10, 10), -4.0, 0.4, 2, 10, 0), ("square", (12, 12), 4.0, 0.3, 2, 10, 0)]
+    for kind, Ls, U, beta, B, sm, db in cases:
+        ctx, chains = make_pair(b200, kind, Ls, U=U, beta=beta, B=B, safe_mult=sm, delay_block=db)
+        check_sweeps(ctx, chains, 1, gtol=1e-9 if Ls[0] >= 10 else GTOL)
+    # traces, forced decisions and the uniform table go through the same kernel
+    ctx, chains = make_pair(b200, "square", (6, 6), U=-4.0, beta=0.5, B=2)
+    ctx.build_stack()
+    for c in chains:
+        c.init()
+    acc, probs, dec = ctx.sweep_traced()
+    for b, c in enumerate(chains):
+        a_ref, p_ref, d_ref = c.local_sweep(trace=True)
+        assert a_ref == acc[b] and np.array_equal(dec[b], d_ref)
+        assert np.allclose(probs[b], p_ref, rtol=1e-9, atol=1e-12)
