@@ -42,7 +42,6 @@ def flops_per_sweep(n, M, C, nb, acc_rate):
 
 
 def build_model(cfg):
-    from oracle import model as OM   # model *inputs* only (lattice -> T); not on the measured path
     kind, Ls, U, beta, B, desc = CONFIGS[cfg]
     return kind, Ls, U, beta, B, desc
 
@@ -188,7 +187,6 @@ def main():
     import torch
     import _b200_loader
     pkg = _b200_loader.load()
-    from oracle import model as OM     # lattice -> hopping matrix inputs only
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the dqmc_b200 path has no CPU fallback")
@@ -198,19 +196,17 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
 
-    T = OM.hopping_matrix(kind, Ls)
-    N, M = T.shape[0], OM.n_slices(beta, DELTA_TAU)
-    fk = OM.choose_field(U)
-    nb = 1 if fk == 0 else 2
-    ranges = OM.generate_chunks(M, SAFE_MULT)
-    C = len(ranges)
-    e2, e2i, eh, ehi = OM.hopping_exponentials(T, DELTA_TAU)
+    # the product's own host mirror builds every input (lattice, hopping matrix, exponentials, ranges, alpha):
+    # nothing under oracle/ is touched on this arm outside the cpu_baseline leg
+    lattice = {"square": pkg.SquareLattice, "honeycomb": pkg.Honeycomb, "chain": pkg.Chain}[kind](*Ls[:1])
+    model = pkg.HubbardModel(lattice, U=U)
+    mc = pkg.DQMC(model, beta=beta, delta_tau=DELTA_TAU, safe_mult=SAFE_MULT, seed=SEED, n_chains=B,
+                  chain_offset=rank * B, device=dev, delay_block=args.delay_block)
+    ctx = mc.ctx
+    T = mc.hopping_matrix
+    N, M, nb, C = ctx.N, ctx.M, ctx.nb, ctx.C
     g = np.random.default_rng(SEED + rank)
     conf = np.asfortranarray(g.choice(np.array([-1, 1], dtype=np.int8), size=(N, M, B)))
-    ctx = pkg.Context(n_sites=N, n_slices=M, field_kind=fk, n_chains=B, ranges=ranges,
-                      alpha=OM.hirsch_alpha(U, DELTA_TAU, fk), hopping_exp_squared=e2, hopping_exp_inv_squared=e2i,
-                      hopping_exp=eh, hopping_exp_inv=ehi, seed=SEED, chain_offset=rank * B, device=dev,
-                      delay_block=args.delay_block)
     ctx.set_conf(conf)
     ctx.build_stack()
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
@@ -313,9 +309,7 @@ def main():
     # ---------------- measurement pass (cfg5's equal-time + unequal-time clause) ----------------
     meas = None
     if args.measure or args.config == "cfg5":
-        from oracle import measure as OMS      # lattice tables only (inputs)
-        nbasis = OM.UNIT_CELLS[kind][0]
-        ctx.set_lattice(OMS.bravais_srctrg2dir(Ls), nbasis, T, U)
+        ctx.set_lattice(np.array(lattice.bravais_srctrg2dir(), dtype=np.int32), len(lattice.unitcell.sites), T, U)
         ctx.measure_equal_time(); ctx.measure_time_integral(SAFE_MULT, DELTA_TAU)          # warm-up
         l1 = ctx.kernel_launches()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
