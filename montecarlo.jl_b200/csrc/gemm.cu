@@ -287,6 +287,9 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
         if (variant == 11) return launch_cfg<64, 64, 32, 32, TA, TB, 8, 3, 5>(p, st);
         if (variant == 12) return launch_cfg<64, 64, 32, 32, TA, TB, 8, 4, 5>(p, st);
         if (variant == 13) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 3, 4>(p, st);
+        if (variant == 20) return launch_cfg<64, 64, 32, 32, TA, TB, 32, 2, 3>(p, st);   // half the CTA barriers per tile
+        if (variant == 21) return launch_cfg<64, 64, 32, 32, TA, TB, 32, 2, 2>(p, st);
+        if (variant == 22) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 4>(p, st);
         if (p.M % 128 == 0 && p.N % 128 == 0) {
             if (variant == 14) return launch_cfg<128, 128, 32, 32, TA, TB, 16, 3, 1>(p, st);   // 16 warps, 1 CTA/SM: 8.0 waves
             if (variant == 15) return launch_cfg<128, 128, 32, 32, TA, TB, 16, 4, 1>(p, st);

@@ -475,3 +475,11 @@ def test_every_update_kernel_variant(b200, version, monkeypatch):
         a_ref, p_ref, d_ref = c.local_sweep(trace=True)
         assert a_ref == acc[b] and np.array_equal(dec[b], d_ref)
         assert np.allclose(probs[b], p_ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind,Ls,U", [("square", (16, 16), -4.0), ("honeycomb", (12, 12), 4.0)])
+def test_sweep_parity_at_bench_sizes(b200, kind, Ls, U):
+    """The kernel geometries of cfg 4 (n = 256, two flavor blocks: update3 with kb = 44, QR levels 256/192/128/64) and
+    cfg 5 (n = 288, one block: kb = 36, cluster-of-8 QR) at short beta: decisions identical, G <= 1e-9 after a sweep."""
+    ctx, chains = make_pair(b200, kind, Ls, U=U, beta=0.3, B=2, safe_mult=2)
+    check_sweeps(ctx, chains, 1, gtol=1e-9)
