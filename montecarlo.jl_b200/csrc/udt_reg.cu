@@ -627,8 +627,14 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
     const double* Tg = T4 + (long long)mat * ngroups * 16;
     double* Ug = p.U + (long long)mat * p.strideU;
 
-    __shared__ __align__(16) double vs[2][4][NV];
-    __shared__ double ts[2][16];
+    // CH blocks of four reflectors per stage: one CTA barrier per 16 reflectors, so the warps drift apart and one
+    // warp's shuffle tree overlaps another's FMAs
+    constexpr int CH = 4;
+    extern __shared__ __align__(16) double fq_sm[];
+    double* vsb = fq_sm;                                 // [2][CH * 4][NV]
+    double* tsb = fq_sm + (size_t)2 * CH * 4 * NV;       // [2][CH][16]
+#define VS(s_, jj_, r_) vsb[((size_t)(s_) * CH * 4 + (jj_)) * NV + (r_)]
+#define TS(s_, gb_, i_) tsb[((s_) * CH + (gb_)) * 16 + (i_)]
 
     double a[8][RPL];
 #pragma unroll
@@ -640,25 +646,31 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
     const int gtop = ctop >> 2;
     const int wtop = (col0 < n) ? (min(n - 1, col0 + 7) >> 2) : -1;   // highest block that touches this warp
     const bool dense = (ldv == NV);
-    auto stage = [&](int g, int s) {                     // block g -> vs[s], ts[s]
-        for (int e = tid; e < 4 * (NV / 2); e += 256) {
-            const int j = e / (NV / 2), r2 = (e - j * (NV / 2)) * 2;
-            const int k = 4 * g + j;
-            if (k < n && (dense || r2 + 1 < ldv)) cp_async16_q(&vs[s][j][r2], Vg + (long long)k * ldv + r2);
-            else { vs[s][j][r2] = 0.0; vs[s][j][r2 + 1] = 0.0; }
+    auto stage = [&](int cidx, int s) {                  // blocks CH cidx .. CH cidx + CH - 1 -> stage s
+        for (int e = tid; e < CH * 4 * (NV / 2); e += 256) {
+            const int jj = e / (NV / 2), r2 = (e - jj * (NV / 2)) * 2;
+            const int k = CH * 4 * cidx + jj;
+            if (k < n && (dense || r2 + 1 < ldv)) cp_async16_q(&VS(s, jj, r2), Vg + (long long)k * ldv + r2);
+            else { VS(s, jj, r2) = 0.0; VS(s, jj, r2 + 1) = 0.0; }
         }
-        if (tid < 16) ts[s][tid] = Tg[(long long)g * 16 + tid];
+        if (tid < CH * 16) {
+            const int g = CH * cidx + (tid >> 4);
+            TS(s, tid >> 4, tid & 15) = (g < ngroups) ? Tg[(long long)g * 16 + (tid & 15)] : 0.0;
+        }
         asm volatile("cp.async.commit_group;\n" ::);
     };
 
-    stage(gtop, 0);
+    const int ctopc = gtop / CH;
+    stage(ctopc, 0);
     const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-    for (int g = gtop; g >= 0; --g) {
-        const int s = (gtop - g) & 1;
+    for (int cidx = ctopc; cidx >= 0; --cidx) {
+        const int s = (ctopc - cidx) & 1;
         asm volatile("cp.async.wait_group 0;\n" ::);
-        __syncthreads();                                 // block g visible; everybody is done with block g + 1
-        if (g > 0) stage(g - 1, s ^ 1);
-        if (g > wtop) continue;                          // warp-uniform
+        __syncthreads();                                 // chunk visible; everybody is done with the previous one
+        if (cidx > 0) stage(cidx - 1, s ^ 1);
+      for (int gb = CH - 1; gb >= 0; --gb) {
+        const int g = CH * cidx + gb;
+        if (g > gtop || g > wtop) continue;              // warp-uniform
         const int r0 = (4 * g) >> 5;                     // first register row a reflector of this block touches
         // ---- W = V^T A: 32 independent chains ---------------------------------------------------
         double d[4][8];
@@ -671,7 +683,7 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
             if (r >= r0) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const double v = vs[s][j][lane + 32 * r];
+                    const double v = VS(s, gb * 4 + j, lane + 32 * r);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) d[j][c] = fma(v, a[c][r], d[j][c]);
                 }
@@ -712,7 +724,7 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
         for (int j = 0; j < 4; ++j) {
             double acc = 0.0;
 #pragma unroll
-            for (int i = j; i < 4; ++i) acc = fma(ts[s][j + 4 * i], w[i], acc);
+            for (int i = j; i < 4; ++i) acc = fma(TS(s, gb, j + 4 * i), w[i], acc);
             y[j] = acc;
         }
         // ---- A -= V Y, four columns at a time (register budget) ------------------------------------
@@ -731,12 +743,13 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
                 if (r >= r0) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const double v = vs[s][j][lane + 32 * r];
+                        const double v = VS(s, gb * 4 + j, lane + 32 * r);
 #pragma unroll
                         for (int c = 0; c < 4; ++c) a[half * 4 + c][r] = fma(v, yy[j][c], a[half * 4 + c][r]);
                     }
                 }
         }
+      }
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -750,6 +763,8 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
         }
     }
 }
+#undef VS
+#undef TS
 
 // ================================================================================================
 // host side
@@ -781,7 +796,14 @@ static cudaError_t launch_formq4(const UdtParams& p, double* T4, cudaStream_t st
     if (e != cudaSuccess) return e;
     const int ctas = p.batch * ((p.n + 63) / 64);
     ++g_kernel_launches;
-    udt_formq4_kernel<RPL><<<(unsigned)ctas, 256, 0, st>>>(p, T4, ngroups);
+    constexpr int smem = (2 * 4 * 4 * RPL * 32 + 2 * 4 * 16) * (int)sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        e = cudaFuncSetAttribute(udt_formq4_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    udt_formq4_kernel<RPL><<<(unsigned)ctas, 256, smem, st>>>(p, T4, ngroups);
     return cudaGetLastError();
 }
 
