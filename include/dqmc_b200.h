@@ -81,6 +81,11 @@ int32_t dqmc_device_count(void);
 /* ---- field configuration: mc.field.conf (fields.jl:363-368) -------------------------------- */
 int32_t dqmc_set_conf(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, const int8_t* conf);
 int32_t dqmc_get_conf(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, int8_t* conf);
+/* compress(field) = BitArray(conf .== 1) / decompress!(field, bits) (fields.jl:331-334), the wire format of the
+ * ConfigRecorder (configurations.jl:92-200): chunks = the UInt64 words of the BitArray (bit i of the column-major
+ * N x M array at chunks[i >> 6], position i & 63), ceil(N M / 64) words per chain, packed on the device. */
+int32_t dqmc_get_conf_packed(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, uint64_t* chunks);
+int32_t dqmc_set_conf_packed(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, const uint64_t* chunks);
 
 /* ---- stack ------------------------------------------------------------------------------- */
 /* reverse_build_stack + propagate (stack.jl:284-308, 605; DQMC.jl:178-179): afterwards

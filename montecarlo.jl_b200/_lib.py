@@ -62,6 +62,8 @@ def load():
         "dqmc_device_count": (i32, []),
         "dqmc_set_conf": (i32, [vp, i32, i32, i8p]),
         "dqmc_get_conf": (i32, [vp, i32, i32, i8p]),
+        "dqmc_get_conf_packed": (i32, [vp, i32, i32, C.POINTER(C.c_uint64)]),
+        "dqmc_set_conf_packed": (i32, [vp, i32, i32, C.POINTER(C.c_uint64)]),
         "dqmc_build_stack": (i32, [vp]),
         "dqmc_forward_build_stack": (i32, [vp]),
         "dqmc_propagate": (i32, [vp, i32]),

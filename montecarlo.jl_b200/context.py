@@ -102,6 +102,22 @@ class Context:
         self._ck(self._L.dqmc_get_conf(self._h, chain0, nchains, out.ctypes.data_as(_lib.i8p)))
         return out
 
+    def get_conf_packed(self, chain0=0, nchains=None):
+        """BitArray(conf .== 1).chunks of every chain (fields.jl:331): uint64 (words, nchains)."""
+        nchains = self.B - chain0 if nchains is None else nchains
+        words = (self.N * self.M + 63) // 64
+        out = np.zeros((words, nchains), dtype=np.uint64, order="F")
+        self._ck(self._L.dqmc_get_conf_packed(self._h, chain0, nchains, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def set_conf_packed(self, chunks, chain0=0):
+        """decompress!(field, bits) (fields.jl:334) on the device."""
+        chunks = np.asfortranarray(chunks, dtype=np.uint64)
+        if chunks.ndim == 1:
+            chunks = chunks.reshape(-1, 1, order="F")
+        assert chunks.shape[0] == (self.N * self.M + 63) // 64
+        self._ck(self._L.dqmc_set_conf_packed(self._h, chain0, chunks.shape[1], chunks.ctypes.data_as(C.POINTER(C.c_uint64))))
+
     # ------------------------------------------------------------------ stack
     def build_stack(self):
         self._ck(self._L.dqmc_build_stack(self._h))

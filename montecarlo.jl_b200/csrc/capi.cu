@@ -514,6 +514,36 @@ int32_t dqmc_get_conf(dqmc_ctx* c, int32_t chain0, int32_t nchains, int8_t* conf
     return DQMC_OK;
 }
 
+// compress / decompress! of the configuration recorder (fields.jl:331-334, configurations.jl): the chunks of
+// BitArray(conf .== 1), ceil(N M / 64) UInt64 per chain
+static int32_t conf_packed(dqmc_ctx* c, int32_t chain0, int32_t nchains, uint64_t* chunks, int pack)
+{
+    const long long nbits = (long long)c->M * c->N, wpc = (nbits + 63) / 64;
+    unsigned long long* d = nullptr;
+    CK(c, cudaMallocAsync((void**)&d, (size_t)wpc * nchains * 8, c->st));
+    if (!pack) CK(c, cudaMemcpyAsync(d, chunks, (size_t)wpc * nchains * 8, cudaMemcpyHostToDevice, c->st));
+    CK(c, launch_conf_bits(c->conf + nbits * chain0, d, nbits, nchains, pack, c->st));
+    if (pack) CK(c, cudaMemcpyAsync(chunks, d, (size_t)wpc * nchains * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaFreeAsync(d, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    return DQMC_OK;
+}
+
+int32_t dqmc_get_conf_packed(dqmc_ctx* c, int32_t chain0, int32_t nchains, uint64_t* chunks)
+{
+    ENTER(c);
+    if (!chunks || !CHAINS_OK(c, chain0, nchains)) FAIL(c, DQMC_ERR_INVALID, "dqmc_get_conf_packed: bad arguments");
+    return conf_packed(c, chain0, nchains, chunks, 1);
+}
+
+int32_t dqmc_set_conf_packed(dqmc_ctx* c, int32_t chain0, int32_t nchains, const uint64_t* chunks)
+{
+    ENTER(c);
+    if (!chunks || !CHAINS_OK(c, chain0, nchains)) FAIL(c, DQMC_ERR_INVALID, "dqmc_set_conf_packed: bad arguments");
+    c->generation += 1;
+    return conf_packed(c, chain0, nchains, const_cast<uint64_t*>(chunks), 0);
+}
+
 int32_t dqmc_build_stack(dqmc_ctx* c)
 {
     ENTER(c);

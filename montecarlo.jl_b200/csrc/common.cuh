@@ -126,4 +126,7 @@ cudaError_t launch_accumulate(const double* G, double* sum, double* sumsq, long 
 cudaError_t launch_scale_add(double* O, const double* A, Scale rs, Scale cs, const double* add, double add_diag,
                              int n, int ld, long long stride, int batch, cudaStream_t st);
 
+// BitArray(conf .== 1) <-> conf for n_chains configurations of nbits sites x slices each
+cudaError_t launch_conf_bits(int8_t* conf, unsigned long long* chunks, long long nbits, int n_chains, int pack, cudaStream_t st);
+
 }  // namespace dqmc

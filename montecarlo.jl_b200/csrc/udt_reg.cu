@@ -767,6 +767,140 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
 #undef TS
 
 // ================================================================================================
+// explicit Q, blocked, with Q held in the DMMA accumulator layout: thread (g, t) of a warp owns rows 8 i + g and the
+// two columns 2 t, 2 t + 1 of the warp's 8 columns.  Per block of four reflectors the dot products W = V^T Q are
+// thread-local over the owned rows (8 chains), reduced over g with a 3-round butterfly; Y = T W; and the update
+// Q -= V Y is ONE m8n8k4 DMMA per 8 rows (A = V rows from shared memory, B = -Y) instead of 64 DFMAs.  ~580
+// instructions per block and warp instead of ~1250: the kernel runs at the FP64 pipe.
+// ================================================================================================
+__device__ __forceinline__ void dmma884q(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int RPL>
+__global__ void __launch_bounds__(256)
+udt_formq5_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
+{
+    constexpr int NV = RPL * 32, RT = RPL * 4, CH = 4;
+    const int n = p.n, ld = p.ld, ldv = p.ldv;
+    const int ctas_per_mat = (n + 63) / 64;
+    const int mat = blockIdx.x / ctas_per_mat, part_i = blockIdx.x - mat * ctas_per_mat;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int col0 = part_i * 64 + warp * 8;             // this warp owns columns col0 .. col0 + 7
+    const double* Vg = p.Vwork + (long long)mat * p.strideV;
+    const double* Tg = T4 + (long long)mat * ngroups * 16;
+    double* Ug = p.U + (long long)mat * p.strideU;
+
+    extern __shared__ __align__(16) double fq_sm[];
+    double* vsb = fq_sm;                                 // [2][CH * 4][NV]
+    double* tsb = fq_sm + (size_t)2 * CH * 4 * NV;       // [2][CH][16]
+#define VS(s_, jj_, r_) vsb[((size_t)(s_) * CH * 4 + (jj_)) * NV + (r_)]
+#define TS(s_, gb_, i_) tsb[((s_) * CH + (gb_)) * 16 + (i_)]
+
+    double q[RT][2];
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) q[i][e] = (col0 + 2 * t4 + e < n && 8 * i + g8 == col0 + 2 * t4 + e) ? 1.0 : 0.0;
+
+    const int ctop = min(n, part_i * 64 + 64) - 1;       // highest column of this CTA
+    const int gtop = ctop >> 2;
+    const int wtop = (col0 < n) ? (min(n - 1, col0 + 7) >> 2) : -1;   // highest block that touches this warp
+    const bool dense = (ldv == NV);
+    auto stage = [&](int cidx, int s) {                  // blocks CH cidx .. CH cidx + CH - 1 -> stage s
+        for (int e = tid; e < CH * 4 * (NV / 2); e += 256) {
+            const int jj = e / (NV / 2), r2 = (e - jj * (NV / 2)) * 2;
+            const int k = CH * 4 * cidx + jj;
+            if (k < n && (dense || r2 + 1 < ldv)) cp_async16_q(&VS(s, jj, r2), Vg + (long long)k * ldv + r2);
+            else { VS(s, jj, r2) = 0.0; VS(s, jj, r2 + 1) = 0.0; }
+        }
+        if (tid < CH * 16) {
+            const int g = CH * cidx + (tid >> 4);
+            TS(s, tid >> 4, tid & 15) = (g < ngroups) ? Tg[(long long)g * 16 + (tid & 15)] : 0.0;
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    const int ctopc = gtop / CH;
+    stage(ctopc, 0);
+    for (int cidx = ctopc; cidx >= 0; --cidx) {
+        const int s = (ctopc - cidx) & 1;
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();                                 // chunk visible; everybody is done with the previous one
+        if (cidx > 0) stage(cidx - 1, s ^ 1);
+        for (int gb = CH - 1; gb >= 0; --gb) {
+            const int g = CH * cidx + gb;
+            if (g > gtop || g > wtop) continue;          // warp-uniform
+            const int i0 = (4 * g) >> 3;                 // first 8-row tile a reflector of this block touches
+            // ---- W = V^T Q, thread-local over the owned rows --------------------------------------------
+            double w[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j][0] = w[j][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < RT; ++i)
+                if (i >= i0) {                           // warp-uniform
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double v = VS(s, gb * 4 + j, 8 * i + g8);
+                        w[j][0] = fma(v, q[i][0], w[j][0]);
+                        w[j][1] = fma(v, q[i][1], w[j][1]);
+                    }
+                }
+            // ---- butterfly over g (lanes 4 g + t): every lane ends with the complete W[:, 2 t .. 2 t + 1] -----------
+#pragma unroll
+            for (int o = 4; o <= 16; o <<= 1)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    w[j][0] += __shfl_xor_sync(0xffffffffu, w[j][0], o);
+                    w[j][1] += __shfl_xor_sync(0xffffffffu, w[j][1], o);
+                }
+            // ---- Y = T W (T upper triangular) ---------------------------------------------------------------
+            double y[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int i = j; i < 4; ++i) {
+                    const double tv = TS(s, gb, j + 4 * i);
+                    a0 = fma(tv, w[i][0], a0); a1 = fma(tv, w[i][1], a1);
+                }
+                y[j][0] = a0; y[j][1] = a1;
+            }
+            // ---- B operand of the update: -Y[j = t][column g]: columns 2 t', 2 t' + 1 live in the lanes with t' = g >> 1 ------
+            double yb = 0.0;
+            {
+                const int src = g8 >> 1;                 // lane (g' = 0, t' = g >> 1)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double v0 = __shfl_sync(0xffffffffu, y[j][0], src);
+                    const double v1 = __shfl_sync(0xffffffffu, y[j][1], src);
+                    if (j == t4) yb = (g8 & 1) ? v1 : v0;
+                }
+                yb = -yb;
+            }
+            // ---- Q -= V Y: one DMMA per 8 rows ----------------------------------------------------------------
+#pragma unroll
+            for (int i = 0; i < RT; ++i)
+                if (i >= i0) dmma884q(q[i][0], q[i][1], VS(s, gb * 4 + t4, 8 * i + g8), yb);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+        const int row = 8 * i + g8;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int col = col0 + 2 * t4 + e;
+            if (row < n && col < n) Ug[row + (long long)col * ld] = q[i][e];
+        }
+    }
+#undef VS
+#undef TS
+}
+
+// ================================================================================================
 // host side
 // ================================================================================================
 template <int RPL>
@@ -797,13 +931,18 @@ static cudaError_t launch_formq4(const UdtParams& p, double* T4, cudaStream_t st
     const int ctas = p.batch * ((p.n + 63) / 64);
     ++g_kernel_launches;
     constexpr int smem = (2 * 4 * 4 * RPL * 32 + 2 * 4 * 16) * (int)sizeof(double);
+    // A/B knob: Q in the DMMA accumulator layout (udt_formq5_kernel) measured SLOWER (1.38 vs 0.96 ms per 296 x 256^2)
+    static const bool v4 = getenv("DQMC_UDT_FORMQ_V5") == nullptr;
     static bool attr_done = false;
     if (!attr_done) {
         e = cudaFuncSetAttribute(udt_formq4_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(udt_formq5_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    udt_formq4_kernel<RPL><<<(unsigned)ctas, 256, smem, st>>>(p, T4, ngroups);
+    if (v4) udt_formq4_kernel<RPL><<<(unsigned)ctas, 256, smem, st>>>(p, T4, ngroups);
+    else udt_formq5_kernel<RPL><<<(unsigned)ctas, 256, smem, st>>>(p, T4, ngroups);
     return cudaGetLastError();
 }
 

@@ -92,13 +92,18 @@ class HirschField:
         self.confs[...] = rng.choice(np.array([-1, 1], dtype=np.int8), size=self.confs.shape)
 
     def compress(self, chain=0):
-        """BitArray(conf .== 1) (fields.jl:331)."""
-        return np.packbits(self.confs[:, :, chain].ravel(order="F") == 1)
+        """compress(field) = BitArray(conf .== 1) (fields.jl:331) -> its chunks: uint64 words, bit i of the
+        column-major array at chunks[i >> 6], position i & 63 (Julia's BitArray layout)."""
+        bits = (self.confs[:, :, chain].ravel(order="F") == 1)
+        by = np.packbits(bits, bitorder="little")
+        by = np.concatenate([by, np.zeros((-len(by)) % 8, dtype=np.uint8)])
+        return by.view("<u8").copy()
 
-    def decompress(self, bits, chain=0):
+    def decompress(self, chunks, chain=0):
+        """decompress!(field, bits) (fields.jl:334): conf = 2 bit - 1."""
         n = self.confs.shape[0] * self.confs.shape[1]
-        c = np.unpackbits(bits)[:n].astype(np.int8) * 2 - 1
-        self.confs[:, :, chain] = c.reshape(self.confs.shape[:2], order="F")
+        bits = np.unpackbits(np.asarray(chunks, dtype="<u8").view(np.uint8), bitorder="little")[:n]
+        self.confs[:, :, chain] = (bits.astype(np.int8) * 2 - 1).reshape(self.confs.shape[:2], order="F")
 
 
 class _StackView:

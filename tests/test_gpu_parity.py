@@ -483,3 +483,21 @@ def test_sweep_parity_at_bench_sizes(b200, kind, Ls, U):
     cfg 5 (n = 288, one block: kb = 36, cluster-of-8 QR) at short beta: decisions identical, G <= 1e-9 after a sweep."""
     ctx, chains = make_pair(b200, kind, Ls, U=U, beta=0.3, B=2, safe_mult=2)
     check_sweeps(ctx, chains, 1, gtol=1e-9)
+
+
+def test_conf_packed_on_device(b200):
+    """dqmc_get_conf_packed / dqmc_set_conf_packed: BitArray(conf .== 1) chunks (fields.jl:331-334) packed on the
+    device equal the host-side compress, for a bit count that is not a multiple of 64."""
+    ctx, chains = make_pair(b200, "square", (7, 7), U=-3.0, beta=1.3, B=3)          # 49 x 13 = 637 bits
+    conf = ctx.get_conf()
+    packed = ctx.get_conf_packed()
+    assert packed.shape == ((49 * 13 + 63) // 64, 3)
+    for b in range(3):
+        flat = conf[:, :, b].ravel(order="F")
+        by = np.packbits(flat == 1, bitorder="little")
+        by = np.concatenate([by, np.zeros((-len(by)) % 8, dtype=np.uint8)])
+        assert np.array_equal(packed[:, b], by.view("<u8"))
+    ctx.set_conf(-conf)
+    ctx.set_conf_packed(packed[:, 1:], chain0=1)
+    now = ctx.get_conf()
+    assert np.array_equal(now[:, :, 0], -conf[:, :, 0]) and np.array_equal(now[:, :, 1:], conf[:, :, 1:])

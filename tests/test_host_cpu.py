@@ -115,3 +115,21 @@ def test_simple_scheduler(b200):
     s = b200.SimpleScheduler(b200.LocalSweep(), b200.GlobalFlip(), b200.LocalSweep(2))
     kinds = [type(s.next()).__name__ for _ in range(8)]
     assert kinds == ["LocalSweep", "GlobalFlip", "LocalSweep", "LocalSweep"] * 2
+
+
+def test_conf_compress_is_julia_bitarray_layout(b200):
+    """fields.jl:331-334: BitArray(conf .== 1); a BitArray stores bit i of the column-major array in chunks[i >> 6]
+    at position i & 63.  Round trip through decompress."""
+    m = b200.HubbardModel(b200.SquareLattice(3), U=1.0)
+    p = b200.DQMCParameters(beta=0.9)
+    f = b200.HirschField("DensityHirschField", p, m, 2)
+    f.rand(np.random.default_rng(3))
+    ch = f.compress(chain=1)
+    flat = f.confs[:, :, 1].ravel(order="F")
+    assert ch.dtype == np.uint64 and len(ch) == (flat.size + 63) // 64
+    for i, v in enumerate(flat):
+        assert ((int(ch[i >> 6]) >> (i & 63)) & 1) == int(v == 1)
+    old = f.confs[:, :, 1].copy()
+    f.confs[:, :, 1] = 1
+    f.decompress(ch, chain=1)
+    assert np.array_equal(f.confs[:, :, 1], old)
