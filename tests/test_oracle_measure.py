@@ -17,55 +17,7 @@ from oracle import ref as R
 
 
 # ------------------------------------------------------------------------------------------------ ED
-def fermion_ops(nmodes):
-    """Jordan-Wigner annihilation operators c_0 .. c_{nmodes-1} as dense matrices."""
-    a = np.array([[0.0, 1.0], [0.0, 0.0]])
-    Z = np.diag([1.0, -1.0])
-    I2 = np.eye(2)
-    ops = []
-    for m in range(nmodes):
-        mats = [Z] * m + [a] + [I2] * (nmodes - m - 1)
-        out = mats[0]
-        for x in mats[1:]:
-            out = np.kron(out, x)
-        ops.append(out)
-    return ops
-
-
-class FreeED:
-    def __init__(self, T, beta):
-        self.N = T.shape[0]
-        N = self.N
-        self.c = fermion_ops(2 * N)                       # mode = site + N * spin
-        H = np.zeros_like(self.c[0])
-        for s in range(2):
-            for i in range(N):
-                for j in range(N):
-                    if T[i, j] != 0.0:
-                        H += T[i, j] * self.c[i + N * s].T @ self.c[j + N * s]
-        self.w, self.V = np.linalg.eigh(H)
-        self.beta = beta
-        self.rho = (self.V * np.exp(-beta * (self.w - self.w.min()))) @ self.V.T
-        self.rho /= np.trace(self.rho)
-
-    def n(self, i, s):
-        return self.c[i + self.N * s].T @ self.c[i + self.N * s]
-
-    def evolve(self, O, tau):
-        ep = (self.V * np.exp(tau * self.w)) @ self.V.T
-        em = (self.V * np.exp(-tau * self.w)) @ self.V.T
-        return ep @ O @ em
-
-    def corr(self, A, B, tau):
-        return np.trace(self.rho @ self.evolve(A, tau) @ B)
-
-    def spin_ops(self, i):
-        N = self.N
-        up, dn = self.c[i], self.c[i + N]
-        mx = up.T @ dn + dn.T @ up
-        my = -1j * (up.T @ dn - dn.T @ up)
-        mz = up.T @ up - dn.T @ dn
-        return mx, my, mz
+from oracle.ed import HubbardED as FreeED  # noqa: E402  (U = 0 here)
 
 
 def free_chain(kind, Ls, beta, field_kind, safe_mult=5):
