@@ -72,12 +72,23 @@ __global__ void prop_error_kernel(const double* A, const double* B, int n, int l
     const int chain = blockIdx.x;
     const double* a = A + (long long)chain * stride_chain;
     const double* b = B + (long long)chain * stride_chain;
-    double m = 0.0;
-    const long long tot = (long long)nb * ld * n;
-    for (long long e = threadIdx.x; e < tot; e += blockDim.x) {
-        const int i = (int)(e % ld);
-        if (i < n) m = fmax(m, fabs(a[e] - b[e]));
-    }
+    // one CTA per chain streams 2 x nb x n x n doubles: four independent column loads per thread keep enough bytes in
+    // flight for one SM's share of HBM bandwidth
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    const int cols = nb * n;
+    for (int i = threadIdx.x % ld; i < n; i += ld)                   // at most one pass: threads own a row, walk columns
+        for (int j = threadIdx.x / ld; j < cols; j += 4 * (blockDim.x / ld)) {
+            const int s = blockDim.x / ld;
+            const long long e0 = (long long)j * ld + i;
+            const bool p1 = j + s < cols, p2 = j + 2 * s < cols, p3 = j + 3 * s < cols;
+            const double a0 = a[e0], b0 = b[e0];
+            const double a1 = p1 ? a[e0 + (long long)s * ld] : 0.0, b1 = p1 ? b[e0 + (long long)s * ld] : 0.0;
+            const double a2 = p2 ? a[e0 + 2LL * s * ld] : 0.0, b2 = p2 ? b[e0 + 2LL * s * ld] : 0.0;
+            const double a3 = p3 ? a[e0 + 3LL * s * ld] : 0.0, b3 = p3 ? b[e0 + 3LL * s * ld] : 0.0;
+            m0 = fmax(m0, fabs(a0 - b0)); m1 = fmax(m1, fabs(a1 - b1));
+            m2 = fmax(m2, fabs(a2 - b2)); m3 = fmax(m3, fabs(a3 - b3));
+        }
+    double m = fmax(fmax(m0, m1), fmax(m2, m3));
     __shared__ double red[32];
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -96,7 +107,12 @@ cudaError_t launch_prop_error(const double* A, const double* B, int n, int ld, l
                               int nb, int n_chains, double thresh, double* stats, cudaStream_t st)
 {
     if (n_chains <= 0) return cudaSuccess;
-    prop_error_kernel<<<(unsigned)n_chains, 256, 0, st>>>(A, B, n, ld, stride_chain, nb, thresh, stats);
+    // threads = a multiple of ld so that every thread owns one row (rows >= n are padding and idle)
+    int threads = (1024 / ld) * ld;
+    if (threads == 0) {   // ld > 1024 does not occur (n <= 512); keep the kernel's ownership rule valid anyway
+        return cudaErrorInvalidValue;
+    }
+    prop_error_kernel<<<(unsigned)n_chains, threads, 0, st>>>(A, B, n, ld, stride_chain, nb, thresh, stats);
     ++g_kernel_launches;
     return cudaGetLastError();
 }

@@ -33,62 +33,88 @@
 /* dense products: src/flavors/DQMC/linalg/real.jl:7-15, 72-102              */
 /* ------------------------------------------------------------------------ */
 
-/* C = A * B   (real.jl:7-15).  m-loop innermost so the compiler vectorises the
- * contiguous index like @turbo does; 4 columns of C per pass as a register
- * tile, no cache blocking (the reference has none either). */
-static void vmul_nn(int n, double *restrict C, const double *restrict A, const double *restrict B)
+/* The reference's products are LoopVectorization @turbo loops (real.jl:7-15, 72-102): the macro register-tiles the
+ * two output indices, keeps the C tile in vector registers across the whole k loop and reassociates reductions; it
+ * does no cache blocking or packing.  The three kernels below restate exactly that (and nothing more: no blocking
+ * over k, no packing), so the CPU baseline is neither flattered nor penalised relative to the package. */
+typedef double v8d __attribute__((vector_size(64), aligned(8), may_alias));
+static inline v8d ld8(const double *p) { return *(const v8d *)p; }
+static inline void st8(double *p, v8d v) { *(v8d *)p = v; }
+
+/* C(i,j) = sum_k A[i + k n] * B[k bk + j bj]: A is contiguous along the output row index, so rows are the vector
+ * dimension.  Tile = 16 rows x 4 columns. */
+static void gemm_rows_contiguous(int n, double *restrict C, const double *restrict A, const double *restrict B,
+                                 size_t bk, size_t bj)
 {
-    int j = 0;
-    for (; j + 4 <= n; j += 4) {
-        double *c0 = C + IDX(0, j, n), *c1 = c0 + n, *c2 = c1 + n, *c3 = c2 + n;
-        for (int i = 0; i < n; ++i) c0[i] = c1[i] = c2[i] = c3[i] = 0.0;
-        for (int k = 0; k < n; ++k) {
-            const double *a = A + IDX(0, k, n);
-            const double b0 = B[IDX(k, j, n)], b1 = B[IDX(k, j + 1, n)];
-            const double b2 = B[IDX(k, j + 2, n)], b3 = B[IDX(k, j + 3, n)];
-            for (int i = 0; i < n; ++i) {
-                const double av = a[i];
-                c0[i] += av * b0; c1[i] += av * b1; c2[i] += av * b2; c3[i] += av * b3;
+    const size_t ld = (size_t)n;
+    for (int j = 0; j < n; j += 4) {
+        const int jw = (n - j < 4) ? n - j : 4;
+        int i = 0;
+        if (jw == 4) {
+            for (; i + 16 <= n; i += 16) {
+                v8d c00 = {0}, c01 = {0}, c10 = {0}, c11 = {0}, c20 = {0}, c21 = {0}, c30 = {0}, c31 = {0};
+                const double *b0 = B + (size_t)j * bj, *b1 = b0 + bj, *b2 = b1 + bj, *b3 = b2 + bj;
+                for (int k = 0; k < n; ++k) {
+                    const v8d a0 = ld8(A + i + k * ld), a1 = ld8(A + i + 8 + k * ld);
+                    const double x0 = b0[k * bk], x1 = b1[k * bk], x2 = b2[k * bk], x3 = b3[k * bk];
+                    c00 += a0 * x0; c01 += a1 * x0; c10 += a0 * x1; c11 += a1 * x1;
+                    c20 += a0 * x2; c21 += a1 * x2; c30 += a0 * x3; c31 += a1 * x3;
+                }
+                double *c = C + i + (size_t)j * ld;
+                st8(c, c00); st8(c + 8, c01); st8(c + ld, c10); st8(c + ld + 8, c11);
+                st8(c + 2 * ld, c20); st8(c + 2 * ld + 8, c21); st8(c + 3 * ld, c30); st8(c + 3 * ld + 8, c31);
             }
         }
-    }
-    for (; j < n; ++j) {
-        double *c0 = C + IDX(0, j, n);
-        for (int i = 0; i < n; ++i) c0[i] = 0.0;
-        for (int k = 0; k < n; ++k) {
-            const double *a = A + IDX(0, k, n);
-            const double b0 = B[IDX(k, j, n)];
-            for (int i = 0; i < n; ++i) c0[i] += a[i] * b0;
-        }
+        for (; i < n; ++i)
+            for (int jj = 0; jj < jw; ++jj) {
+                double sacc = 0.0;
+                const double *bb = B + (size_t)(j + jj) * bj;
+                for (int k = 0; k < n; ++k) sacc += A[i + k * ld] * bb[k * bk];
+                C[i + (size_t)(j + jj) * ld] = sacc;
+            }
     }
 }
+
+/* C = A * B   (real.jl:7-15) */
+static void vmul_nn(int n, double *restrict C, const double *restrict A, const double *restrict B)
+{ gemm_rows_contiguous(n, C, A, B, 1, (size_t)n); }
 
 /* C = A * B'   (real.jl:72-81) */
 static void vmul_nt(int n, double *restrict C, const double *restrict A, const double *restrict B)
-{
-    for (int j = 0; j < n; ++j) {
-        double *c0 = C + IDX(0, j, n);
-        for (int i = 0; i < n; ++i) c0[i] = 0.0;
-        for (int k = 0; k < n; ++k) {
-            const double *a = A + IDX(0, k, n);
-            const double b0 = B[IDX(j, k, n)];
-            for (int i = 0; i < n; ++i) c0[i] += a[i] * b0;
-        }
-    }
-}
+{ gemm_rows_contiguous(n, C, A, B, (size_t)n, 1); }
 
-/* C = A' * B   (real.jl:82-91): dot products of contiguous columns */
+/* C = A' * B   (real.jl:82-91): both operands are contiguous along k, so k is the vector dimension: a 4 x 4 tile of
+ * vector partial sums, reduced at the end. */
 static void vmul_tn(int n, double *restrict C, const double *restrict A, const double *restrict B)
 {
-    for (int j = 0; j < n; ++j) {
-        const double *b = B + IDX(0, j, n);
-        for (int i = 0; i < n; ++i) {
-            const double *a = A + IDX(0, i, n);
-            double s = 0.0;
-            for (int k = 0; k < n; ++k) s += a[k] * b[k];
-            C[IDX(i, j, n)] = s;
+    const size_t ld = (size_t)n;
+    const int n4 = n & ~3, k8 = n & ~7;
+    for (int j = 0; j < n4; j += 4)
+        for (int i = 0; i < n4; i += 4) {
+            v8d acc[4][4];
+            for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) acc[a][b] = (v8d){0};
+            const double *a0 = A + i * ld, *b0 = B + j * ld;
+            for (int k = 0; k < k8; k += 8) {
+                const v8d x0 = ld8(a0 + k), x1 = ld8(a0 + ld + k), x2 = ld8(a0 + 2 * ld + k), x3 = ld8(a0 + 3 * ld + k);
+                for (int b = 0; b < 4; ++b) {
+                    const v8d y = ld8(b0 + b * ld + k);
+                    acc[0][b] += x0 * y; acc[1][b] += x1 * y; acc[2][b] += x2 * y; acc[3][b] += x3 * y;
+                }
+            }
+            for (int a = 0; a < 4; ++a)
+                for (int b = 0; b < 4; ++b) {
+                    double sacc = 0.0;
+                    for (int l = 0; l < 8; ++l) sacc += acc[a][b][l];
+                    for (int k = k8; k < n; ++k) sacc += a0[a * ld + k] * b0[b * ld + k];
+                    C[(i + a) + (size_t)(j + b) * ld] = sacc;
+                }
         }
-    }
+    for (int j = 0; j < n; ++j)
+        for (int i = (j < n4 ? n4 : 0); i < n; ++i) {
+            double sacc = 0.0;
+            for (int k = 0; k < n; ++k) sacc += A[k + i * ld] * B[k + j * ld];
+            C[i + j * ld] = sacc;
+        }
 }
 
 /* C = A * Diagonal(d)  (real.jl:16-20) */

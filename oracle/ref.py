@@ -36,10 +36,25 @@ def build(force: bool = False) -> Path:
     hdr = _HERE.parent / "include" / "dqmc_rng.h"
     deps = [src, _HERE / "dqmc_ref_ut.inc.c", _HERE / "dqmc_ref_global.inc.c", hdr]
     stale = (not so.exists()) or so.stat().st_mtime < max(d.stat().st_mtime for d in deps)
+    # the library is compiled -march=native and travels with the tree: rebuild when the host CPU is not the one it
+    # was built on (an illegal-instruction fault is the alternative)
+    tag, cpu = _HERE / "libdqmc_ref.so.cpu", _cpu_signature()
+    if not stale and (not tag.exists() or tag.read_text() != cpu):
+        stale = True
     if force or stale:
         subprocess.check_call(["make", "-C", str(_HERE), "-B", "libdqmc_ref.so"],
                               stdout=subprocess.DEVNULL)
+        tag.write_text(cpu)
     return so
+
+
+def _cpu_signature() -> str:
+    import hashlib
+    try:
+        lines = [l for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags"))][:2]
+    except OSError:
+        lines = []
+    return hashlib.sha1("".join(lines).encode()).hexdigest()
 
 
 def lib():
