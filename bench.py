@@ -31,7 +31,7 @@ CONFIGS = {
     "cfg2": ("square", (8, 8), 4.0, 10.0, 256, "attractive Hubbard 8x8, U=4, beta=10, 256 chains/GPU"),
     "cfg3": ("square", (12, 12), -4.0, 8.0, 128, "repulsive Hubbard 12x12, U=-4, beta=8, 128 chains/GPU"),
     "cfg4": ("square", (16, 16), -4.0, 16.0, 148, "repulsive Hubbard 16x16, U=-4, beta=16, dtau=0.1 (N=256, M=160)"),
-    "cfg5": ("honeycomb", (12, 12), 4.0, 10.0, 64, "attractive Hubbard honeycomb L=12 (N=288), U=4, beta=10"),
+    "cfg5": ("honeycomb", (12, 12), 4.0, 10.0, 148, "attractive Hubbard honeycomb L=12 (N=288), U=4, beta=10"),
     # the only timings the reference's docs state (docs/src/DQMC/fields.md:49-56, ~1470 and ~588 sweeps/s on unstated
     # hardware): run with --impl reference to anchor the CPU port against them
     "anchor6a": ("square", (6, 6), 1.0, 1.0, 256, "anchor: attractive Hubbard 6x6, U=1, beta=1 (DensityHirschField)"),
