@@ -2,7 +2,7 @@
 chains.  Chains never interact, so a sweep of context A can overlap with context B's: latency-bound kernels (UDT steps, the
 serial phase of the local update) leave issue slots and whole SMs idle that the other context's DMMA GEMMs can use.
 
-    python scripts/exp_contexts.py [--config cfg4] [--chains 148] [--contexts 2] [--sweeps 3]
+    python profiles/exp_contexts.py [--config cfg4] [--chains 148] [--contexts 2] [--sweeps 3]
 """
 import argparse
 import sys
