@@ -328,9 +328,7 @@ static cudaError_t sweep_spatial(dqmc_ctx* c, int step, const double* d_unif, lo
     p.kb = c->kb;
     c->generation += 1;
     if (c->update_version == 1) return launch_update(p, c->st);
-    if (c->update_version == 3) return launch_update3(p, c->st);
-    p.Ufac = c->upd_U; p.Wfac = c->upd_W; p.ldf = c->ld; p.strideF = (long long)c->ld * c->kb;
-    return launch_update2(p, c->st);
+    return launch_update3(p, c->st);
 }
 
 // local_sweep (local_updates.jl:7-14); tables are device pointers [B][2M][N] or null
@@ -430,18 +428,15 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     c->seed = d->seed; c->chain_offset = d->chain_offset; c->device = d->device;
     c->ld = (c->N + 1) & ~1; c->ms = (long long)c->ld * c->N; c->nmat = c->B * c->nb;
     c->ldv = ((c->N + 31) / 32) * 32;
-    // update3.cu (submatrix form) is the default; update.cu (delayed rank-kb factors, kb = 24 at cfg 4) and update2.cu
-    // (GEMM flush, measured slower) stay selectable for A/B runs
+    // update3.cu (submatrix form) for n >= 96, update.cu (delayed rank-kb factors) below; DQMC_UPDATE_V1 / _V3 force
+    // one of them for A/B runs
     // (measured: update3 wins from n = 144 up -- cfg 3 / 4 / 5 -- and loses at n = 64, where its per-block overheads
     // outweigh the saved flush passes: cfg 2 5195 vs 5970 sweeps/s)
-    c->update_version = getenv("DQMC_UPDATE_V1") ? 1 : (getenv("DQMC_UPDATE_V2") ? 2 : (getenv("DQMC_UPDATE_V3") ? 3 : (c->N >= 96 ? 3 : 1)));
+    c->update_version = getenv("DQMC_UPDATE_V1") ? 1 : (getenv("DQMC_UPDATE_V3") ? 3 : (c->N >= 96 ? 3 : 1));
     if (c->update_version == 1) {
         c->kb = d->delay_block > 0 ? ((d->delay_block + 3) & ~3) : update_pick_kb(c->N, c->nb);
         const int kmax = update_pick_kb(c->N, c->nb);
         if (c->kb > kmax) c->kb = kmax;
-    } else if (c->update_version == 2) {
-        c->kb = update2_pick_kb(c->N, c->nb);
-        if (d->delay_block > 0) { int kb = 8; while (kb < d->delay_block && kb < c->kb) kb *= 2; c->kb = kb; }
     } else {
         c->kb = update3_pick_kb(c->N, c->nb);
         if (d->delay_block > 0) c->kb = std::min(c->kb, (d->delay_block + 3) & ~3);
@@ -464,7 +459,6 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     A_(udt_scratch, (size_t)c->nmat * udt_reg_scratch_doubles(c->N, c->ld));
     A_(udt_iscratch, (size_t)c->nmat * udt_reg_scratch_ints(c->N));
     A_(pivot, vec); A_(accepted, (size_t)c->B);
-    if (c->update_version == 2) { A_(upd_U, (size_t)c->nmat * c->ld * c->kb); A_(upd_W, (size_t)c->nmat * c->ld * c->kb); }
     A_(stats_neg, (size_t)c->B * 4); A_(stats_prop, (size_t)c->B * 4);
     c->obs_len = 1 + 2 * (long long)c->nb * c->ms;
     A_(obs, (size_t)c->obs_len);

@@ -103,13 +103,9 @@ struct UpdateParams {
     unsigned char* decisions;                // optional trace of accept decisions
     long long tstride;                       // per-chain stride of forced / probs / decisions
     int kb;                                  // delay block size
-    // update2.cu only: full-length delayed factors of the current block, n x kb per matrix (leading dimension ldf)
-    double* Ufac; double* Wfac; long long strideF; int ldf;
 };
 cudaError_t launch_update(const UpdateParams& p, cudaStream_t st);
 int update_pick_kb(int n, int nb);
-cudaError_t launch_update2(const UpdateParams& p, cudaStream_t st);   // block-restricted proposals + GEMM flush
-int update2_pick_kb(int n, int nb);
 cudaError_t launch_update3(const UpdateParams& p, cudaStream_t st);   // submatrix form: G0 + Bc X Br, in-kernel flush
 int update3_pick_kb(int n, int nb);
 

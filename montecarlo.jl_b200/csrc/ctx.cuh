@@ -31,8 +31,7 @@ struct dqmc_ctx {
     double *greens = nullptr, *greens_temp = nullptr, *Ul = nullptr, *Ur = nullptr, *Tl = nullptr, *Tr = nullptr;
     double *tmp1 = nullptr, *tmp2 = nullptr, *curr_U = nullptr, *Dl = nullptr, *Dr = nullptr;
     double* Dgreens = nullptr;         // D of the last Green's function calculation: det(greens) = 1 / prod(Dgreens)
-    double *upd_U = nullptr, *upd_W = nullptr;   // delayed factors of update2.cu, nmat x ld x kb each
-    int update_version = 3;            // 3: update3.cu (default); DQMC_UPDATE_V1 -> update.cu; DQMC_UPDATE_V2 -> update2.cu
+    int update_version = 3;            // 3: update3.cu (n >= 96), 1: update.cu; DQMC_UPDATE_V1 / DQMC_UPDATE_V3 force one
     int8_t* conf_backup = nullptr;     // temp_conf of the global updates (fields.jl: temp_conf)
     double *Vwork = nullptr, *tau = nullptr, *udt_scratch = nullptr;
     int* pivot = nullptr; int* udt_iscratch = nullptr;

@@ -141,7 +141,7 @@ gemm_kernel(const GemmParams p)
     const int KTr = (p.K + BK - 1) / BK;
     const int KT = KTr * (p.krep > 0 ? p.krep : 1);   // krep > 1: timing experiment only (repeats the k loop)
 
-    // C read-modify-write without scalings (the rank-k flush of update2.cu, the panel updates of rdivp.cu):
+    // C read-modify-write without scalings (the panel updates of rdivp.cu):
     // the accumulators start from beta / alpha * C, so the loads of C overlap the main loop instead of sitting
     // behind it in the epilogue.  Exact for alpha = +-1.
     const bool preload = (p.beta != 0.0) && !has_rs && !has_cs && !p.add_diag && (p.alpha == 1.0 || p.alpha == -1.0);

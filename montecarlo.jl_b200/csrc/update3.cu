@@ -394,7 +394,10 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
                     const int xa = (ap < k) ? sh->xs[ap] : 0;               // X column ap is zero for ap >= k
                     double bf[4];
 #pragma unroll
-                    for (int nj = 0; nj < 4; ++nj) bf[nj] = P2[(size_t)xa * ldu + c0 + nj * 8 + g8];
+                    for (int nj = 0; nj < 4; ++nj) {         // columns >= n are never stored: do not read past the row
+                        const int cc = c0 + nj * 8 + g8;    // (another warp writes what follows it)
+                        bf[nj] = (cc < n) ? P2[(size_t)xa * ldu + cc] : 0.0;
+                    }
 #pragma unroll
                     for (int mi = 0; mi < U3_KBT / 8; ++mi)
                         if (mi * 8 < 4 * k4) {              // uniform

@@ -451,12 +451,12 @@ def test_check_propagation_error_off_is_identical(b200):
 
 
 # ===================================================================== every local-update kernel variant
-@pytest.mark.parametrize("version", [1, 2, 3])
+@pytest.mark.parametrize("version", [1, 3])
 def test_every_update_kernel_variant(b200, version, monkeypatch):
-    """The library picks update.cu (delayed rank-kb factors) below n = 96 and update3.cu (submatrix form) above;
-    update2.cu (GEMM flush) is opt-in.  All three must take the oracle's decisions on every geometry: one / two
+    """The library picks update.cu (delayed rank-kb factors) below n = 96 and update3.cu (submatrix form) above.
+    Both must take the oracle's decisions on every geometry: one / two
     flavor blocks, odd n, ragged delay blocks, single range, and n > kb (several blocks per slice)."""
-    for v in (1, 2, 3):
+    for v in (1, 3):
         monkeypatch.delenv(f"DQMC_UPDATE_V{v}", raising=False)
     monkeypatch.setenv(f"DQMC_UPDATE_V{version}", "1")
     cases = [("square", (4, 4), 4.0, 1.0, 3, 10, 0), ("square", (6, 6), -4.0, 1.0, 2, 5, 0),
