@@ -28,6 +28,18 @@ def test_vmul_variants(ta, tb):
     assert np.allclose(R.vmul(A, B, ta, tb), ref, atol=100 * np.finfo(float).eps, rtol=0)
 
 
+@pytest.mark.parametrize("n", [1, 3, 7, 15, 16, 17, 23, 36, 50, 64, 100])
+def test_vmul_register_tiles_and_tails(n):
+    """The oracle's products are register-tiled (16 x 4 row-vector tiles, 4 x 4 dot-product tiles, 8-wide k vectors): every
+    tail combination must still be the plain product."""
+    g = rng(100 + n)
+    A, B = g.standard_normal((n, n)), g.standard_normal((n, n))
+    for ta in (0, 1):
+        for tb in (0, 1):
+            ref = (A.T if ta else A) @ (B.T if tb else B)
+            assert np.allclose(R.vmul(A, B, ta, tb), ref, atol=1e-13 * max(1.0, np.abs(ref).max()), rtol=0), (n, ta, tb)
+
+
 # ------------------------------------------------------------ test/linalg.jl:97-131
 @pytest.mark.parametrize("kind", ["random", "rank1"])
 def test_udt_identities_and_rdivp(kind):
