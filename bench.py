@@ -50,6 +50,21 @@ def build_model(cfg):
     return kind, Ls, U, beta, B, desc
 
 
+def config_dict(cfg, B, world):
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm (it names the workload;
+    what the CPU arm actually sampled is described in its cpu_baseline.sample)."""
+    kind, Ls, U, beta, _, desc = CONFIGS[cfg]
+    nbasis = 2 if kind == "honeycomb" else 1
+    N = nbasis * int(np.prod(Ls if len(Ls) > 1 else Ls))
+    M = int(round(beta / DELTA_TAU))
+    nb = 2 if U < 0 else 1
+    C = -(-M // SAFE_MULT)
+    return {"workload": f"{cfg}: {desc}", "chains_per_gpu": B, "n_sites": N, "n_slices": M,
+            "flavor_blocks": nb, "delta_tau": DELTA_TAU, "safe_mult": SAFE_MULT, "U": U,
+            "l2": "inputs larger than L2 (per-GPU state %.1f GB)" % (ctx_bytes(N, M, C, nb, B) / 1e9),
+            "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"}
+
+
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------
@@ -98,6 +113,76 @@ def run_cpu_measure(cfg):
     return {"time_integral_s_per_chain": float(np.mean(per)), "cores": cores, "chains": cores, "wall_s": time.time() - t0,
             "time_integral_passes_per_s": cores / float(np.max(per)), "kind": "port",
             "sample": f"{cores} chains (one per host core), one TimeIntegral pass each; oracle C iterator + numpy Wick kernels"}
+
+
+def make_mc(pkg, cfg, B, dev, chain_offset=0, seed=SEED, rank=0):
+    """The product's host mirror builds every input of a configuration (nothing under oracle/ is touched)."""
+    kind, Ls, U, beta, _, _ = build_model(cfg)
+    lattice = {"square": pkg.SquareLattice, "honeycomb": pkg.Honeycomb, "chain": pkg.Chain}[kind](*Ls[:1])
+    model = pkg.HubbardModel(lattice, U=U)
+    mc = pkg.DQMC(model, beta=beta, delta_tau=DELTA_TAU, safe_mult=SAFE_MULT, seed=seed, n_chains=B,
+                  chain_offset=chain_offset, device=dev)
+    g = np.random.default_rng(seed + rank)
+    conf = np.asfortranarray(g.choice(np.array([-1, 1], dtype=np.int8), size=(mc.ctx.N, mc.ctx.M, B)))
+    mc.ctx.set_conf(conf)
+    return mc, lattice, conf
+
+
+def quick_config(pkg, torch, cfg, dev, rank, world, nsweeps, max_over_ranks):
+    """Device-resident sweeps/s of one of the other BASELINE configurations (same timing rules, fewer sweeps)."""
+    B = CONFIGS[cfg][4]
+    mc, _, _ = make_mc(pkg, cfg, B, dev, chain_offset=rank * B, rank=rank)
+    ctx = mc.ctx
+    ctx.build_stack()
+    for _ in range(3):
+        ctx.sweep(1)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.kernel_launches()
+    e0.record(stream)
+    acc = 0
+    for _ in range(nsweeps):
+        acc += int(ctx.sweep(1).sum())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    out = {"workload": f"{cfg}: {CONFIGS[cfg][5]}", "chains_per_gpu": B, "chains_total": B * world, "steps": nsweeps,
+           "value": world * B * nsweeps / (ms * 1e-3), "unit": "sweeps/s", "ms_per_step": ms / nsweeps,
+           "acceptance": acc / (B * nsweeps * 2.0 * ctx.N * ctx.M), "gpu_launches_per_step": (ctx.kernel_launches() - l0) / nsweeps}
+    ctx.close()
+    return out
+
+
+def parity_leg(pkg, cfg, dev):
+    """cpu_baseline leg only (the one place bench.py may execute oracle/): ONE oracle chain x ONE full sweep of the bench
+    workload against the device under the shared counter RNG -- decisions, G at sweep end (vs the oracle and vs the
+    extended-precision arbiter oracle/truth_ld.c), propagation-error counts.  The oracle here is the checker."""
+    from oracle import model as OM, ref as OR, truth as TR
+    kind, Ls, U, beta, _, _ = build_model(cfg)
+    mc, _, conf = make_mc(pkg, cfg, 2, dev, seed=SEED + 1)
+    ctx = mc.ctx
+    ctx.build_stack()
+    c = OR.RefChain(OM.hopping_matrix(kind, Ls), U=U, beta=beta, delta_tau=DELTA_TAU, safe_mult=SAFE_MULT,
+                    seed=SEED + 1, chain_id=0, conf=conf[:, :, 0])
+    c.init()
+    t0 = time.time()
+    a_ref, p_ref, d_ref = c.local_sweep(trace=True)
+    t_oracle = time.time() - t0
+    acc, probs, dec = ctx.sweep_traced()
+    G = ctx.greens()[:, :, :, 0]
+    truth = TR.greens_truth_chain(c, chunk=10)
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    st = ctx.stats()[0]
+    out = {"config": cfg, "decisions": int(dec[0].size), "decisions_identical": bool(np.array_equal(dec[0], d_ref)),
+           "decision_mismatches": int((dec[0] != d_ref).sum()), "accepted_dev": int(acc[0]), "accepted_oracle": int(a_ref),
+           "conf_identical": bool(np.array_equal(ctx.get_conf()[:, :, 0], c.get_conf())),
+           "G_dev_vs_oracle": rel(G, c.greens), "G_dev_vs_truth": rel(G, truth), "G_oracle_vs_truth": rel(c.greens, truth),
+           "tolerance": 1e-10, "prop_count_dev": int(st["prop_count"]), "prop_count_oracle": int(c.stats["prop_count"]),
+           "oracle_sweep_s": t_oracle,
+           "truth": "oracle/truth_ld.c: x87 long double, independent stabilisation (role of BigFloat in the reference's tests)"}
+    ctx.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -159,6 +244,8 @@ def main():
     ap.add_argument("--delay-block", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short device-resident runs of the other BASELINE configurations")
     ap.add_argument("--measure", action="store_true",
                     help="also time one equal-time + one TimeIntegral measurement pass (device Wick kernels and the "
                          "CombinedGreensIterator) and the oracle's CPU time for the same; default for cfg5")
@@ -173,15 +260,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warm = max(1, args.steps), 0 if args.config in ("cfg3", "cfg4", "cfg5") else min(args.warmup, 1)
+        steps, warm = max(1, args.steps), max(0, args.warmup)
         r = run_cpu(args.config, steps, warm)
         line = {"impl": "reference", "metric": "DQMC sweeps/sec (all chains)", "value": r["value"], "unit": "sweeps/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * r["seconds"] / steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"{args.config}: {desc}", "chains": r["chains"], "delta_tau": DELTA_TAU,
-                           "safe_mult": SAFE_MULT},
+                "config": config_dict(args.config, B, args.gpus),
                 "cpu_baseline": {"value": r["value"], "unit": "sweeps/s", "cores": r["cores"], "kind": "port",
-                                 "sample": f"{r['chains']} chains (one per host core) x {steps} sweep(s); C port of the "
+                                 "sample": f"{r['chains']} chains (one per host core) x {steps} sweep(s) after {warm} warm-up "
+                                           "sweep(s); a step = one sweep of every sampled chain; C port of the "
                                            "reference's loops (oracle/dqmc_ref.c) -- Julia is not in the image"},
                 "e2e": {"value": r["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "acceptance": r["acceptance"], "gpu_launches": 0}
@@ -214,6 +301,12 @@ def main():
     ctx.set_conf(conf)
     ctx.build_stack()
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+    if world > 1:
+        # the path's only collective (final observable reduction) goes through the library's own NCCL communicator
+        # on the context's stream; torch.distributed only ships the 128-byte id and does the timing barriers
+        ids = [pkg.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(world, rank, ids[0])
 
     def barrier():
         if world > 1:
@@ -250,9 +343,8 @@ def main():
     for _ in range(K):
         acc_total += int(ctx.sweep(1).sum())
     ctx.accumulate_greens()
-    if world > 1:      # the only collective of the path: final observable reduction over NVLink
-        buf = ctx.observable_tensor(torch)
-        dist.all_reduce(buf)
+    if world > 1:      # the only collective of the path: final observable reduction over NVLink (dqmc_reduce_observables)
+        ctx.reduce_observables()
     e1.record(stream)
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -297,13 +389,49 @@ def main():
             avg_ms = gm["ms"] / max(gm["count"], 1)
             achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
             total_ms = sum(v["ms"] for v in prof.values())
-            traffic = None
-            tf = ROOT / "profiles" / "r1_traffic.json"
-            if tf.exists() and args.config == "cfg4" and B == 148:      # the ncu capture is of exactly this launch shape
-                traffic = json.loads(tf.read_text())["gemm_kernel"]["dram_bytes_per_launch"]
+            traffic, traffic_src = None, None
+            tf = ROOT / "profiles" / "traffic.json"      # ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch)
+            tj = json.loads(tf.read_text()) if tf.exists() else {}
+            shape_key = f"{args.config}:{B}"
+            tk = tj.get(shape_key, {})
+            if "gemm" in tk:
+                traffic, traffic_src = tk["gemm"]["dram_bytes_per_launch"], tk["gemm"]["source"]
+            a_rate = acc_rate
+            udt, upd = prof["udt"], prof["update"]
+            udt_flops = (10.0 / 3.0) * N ** 3 * B * nb                    # QR 4/3 + norms 2/3 + form-Q 4/3
+            upd_flops = 2.0 * N * N * nb * (a_rate * N) * B               # 2 n^2 per accepted flip and flavor block
+            upd_bytes = 2.0 * B * nb * N * N * 8                           # one read + one write of every G
+            hbm_peak = None
+            mp = ROOT / "MEASURED_PEAKS.json"
+            if mp.exists():
+                hbm_peak = json.loads(mp.read_text()).get("hbm_gbs")
+            hbm_peak = hbm_peak or 6552.0
+            def per_class(c, flops, extra=None):
+                avg = c["ms"] / max(c["count"], 1)
+                tfl = flops / (avg * 1e-3) / 1e12 if avg > 0 else None
+                d = {"launches_or_calls": c["count"], "avg_ms": avg, "ms_per_step": c["ms"] / K,
+                     "share_of_step": c["ms"] / total_ms if total_ms else None,
+                     "achieved_tflops": tfl, "frac_of_fp64_peak": (tfl / p64) if (tfl and p64) else None,
+                     "algorithmic_flops": flops}
+                if extra:
+                    d.update(extra)
+                return d
+            upd_avg = upd["ms"] / max(upd["count"], 1)
+            classes = {
+                "gemm": per_class(gm, flops_per_launch, {"dram_bytes_per_launch": traffic, "dram_source": traffic_src}),
+                "udt": per_class(udt, udt_flops, {"dram_bytes_per_call": tk.get("udt", {}).get("dram_bytes_per_launch"),
+                                                  "dram_source": tk.get("udt", {}).get("source")}),
+                "update": per_class(upd, upd_flops, {
+                    "algorithmic_bytes": upd_bytes,
+                    "achieved_gbs_algorithmic": upd_bytes / (upd_avg * 1e-3) / 1e9 if upd_avg > 0 else None,
+                    "frac_of_hbm_peak_algorithmic": upd_bytes / (upd_avg * 1e-3) / 1e9 / hbm_peak if upd_avg > 0 else None,
+                    "dram_bytes_per_launch": tk.get("update", {}).get("dram_bytes_per_launch"),
+                    "dram_source": tk.get("update", {}).get("source")}),
+            }
             roof = {"bound": "tensor", "kernel": "gemm_kernel (FP64 DMMA batched GEMM)", "achieved": achieved,
                     "peak": p64, "unit": "TFLOP/s", "frac": achieved / p64 if p64 else None, "traffic": traffic,
-                    "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum; algorithmic "
+                    "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                    f"{traffic_src or 'no capture of this launch shape committed'}; algorithmic "
                                     f"{3 * B * nb * N * N * 8 / 1e6:.0f} MB = two operands read + one result written)",
                     "peak_source": "measured in this run: cuBLAS DGEMM (torch.matmul f64 8192^3, best of 5); "
                                    "MEASURED_PEAKS.json has no FP64 entry",
@@ -311,6 +439,7 @@ def main():
                     "launches": gm["count"], "avg_launch_ms": avg_ms,
                     "share_of_step": gm["ms"] / total_ms if total_ms else None,
                     "kernel_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
+                    "classes": classes,
                     "whole_sweep_frac_of_fp64_peak": (flops_per_sweep(N, M, C, nb, acc_rate) * value / world / 1e12) / p64 if p64 else None}
 
     # ---------------- measurement pass (cfg5's equal-time + unequal-time clause) ----------------
@@ -342,10 +471,7 @@ def main():
         line = {"metric": "DQMC sweeps/sec (all chains)", "value": value, "unit": "sweeps/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"{args.config}: {desc}", "chains_per_gpu": B, "n_sites": N, "n_slices": M,
-                           "flavor_blocks": nb, "delta_tau": DELTA_TAU, "safe_mult": SAFE_MULT, "U": U,
-                           "l2": "inputs larger than L2 (per-GPU state %.1f GB)" % (ctx_bytes(N, M, C, nb, B) / 1e9),
-                           "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
+                "config": config_dict(args.config, B, world),
                 "acceptance": acc_rate, "gpu_launches": int(launches), "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K},
@@ -353,6 +479,20 @@ def main():
                 "flops_per_sweep_per_chain": flops_per_sweep(N, M, C, nb, acc_rate)}
         if meas is not None:
             line["measurement"] = meas
+    # ---------------- the other BASELINE configurations, device-resident, same timing rules (short) ----------
+    others = None
+    if args.config == "cfg4" and not args.no_other_configs:
+        others = {}
+        for cfg2, nsw in (("cfg1", 100), ("cfg2", 20), ("cfg3", 5), ("cfg5", 3)):
+            others[cfg2] = quick_config(pkg, torch, cfg2, dev, rank, world, nsw, max_over_ranks)
+    if rank == 0:
+        if others is not None:
+            if world == 1 and not args.no_cpu_baseline:      # rows "configs 1-2 faster than the reference": CPU port beside them
+                for cfg2 in ("cfg1", "cfg2"):
+                    r1 = run_cpu(cfg2, 20 if cfg2 == "cfg2" else 400, 1, max_chains=1 if cfg2 == "cfg1" else None)
+                    others[cfg2]["cpu_port"] = {"value": r1["value"], "cores": r1["cores"], "chains": r1["chains"],
+                                                "sweeps_per_chain": r1["sweeps_per_chain"], "seconds": r1["seconds"]}
+            line["other_configs"] = others
         if world == 1 and not args.no_cpu_baseline:
             r = run_cpu(args.config, 1, 0)
             if r["seconds"] < 4.0:      # bounded sample of about 10 s: size it from the first sweep
@@ -361,6 +501,7 @@ def main():
                                     "sample": f"{r['chains']} chains (one per host core) x {r['sweeps_per_chain']} sweep(s) "
                                               f"each of the same workload, {r['seconds']:.1f} s; oracle/dqmc_ref.c "
                                               "(C port, Julia absent)"}
+            line["parity"] = parity_leg(pkg, args.config, dev)
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

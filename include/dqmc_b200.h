@@ -62,6 +62,8 @@ typedef struct dqmc_desc {
     int64_t chain_offset;             /* global index of chain 0 (multi-GPU sharding)           */
     int32_t device;                   /* CUDA device ordinal                                    */
     int32_t delay_block;              /* sites per delayed-update block, 0 = auto               */
+    int32_t update_variant;           /* sweep_spatial kernel: 0 = auto (by lattice size), 1 = delayed rank-k factors
+                                         (update.cu), 3 = submatrix form (update3.cu); same decisions either way   */
 } dqmc_desc;
 
 /* MagnitudeStats (src/flavors/DQMC/statistics.jl:9-38) per chain. */
@@ -118,10 +120,14 @@ int32_t dqmc_set_sweep_index(dqmc_ctx* ctx, int64_t sweep);
  * caller: GlobalShuffle, SpatialShuffle, ...) or NULL for GlobalFlip (:237-248, conf -> -conf).  The weight ratio
  * is det(G_old) / det(G_new) from the diagonal factors (inv_det :70-137, propose_global_from_conf :147-179);
  * accepted chains keep the proposal, rejected ones their old configuration; afterwards the stack is rebuilt
- * (accept_global! :181-198) and sits at (slice 1, direction +1).  uniforms: [n_chains] or NULL (counter RNG with
- * step = 2M, site = 0, dqmc_rng.h).  accepted / probs: [n_chains], may be NULL; probs = |exp(-dE_boson) detratio|. */
+ * (accept_global! :181-198) and sits at (slice 1, direction +1).  uniforms: [n_chains] or NULL: counter RNG
+ * (dqmc_rng.h) with sweep = the sweep index, step = 2M and site = the running index of the global update on this
+ * context (0, 1, 2, ...: two global updates between local sweeps never share a uniform).
+ * accepted / probs: [n_chains], may be NULL; probs = |exp(-dE_boson) detratio|. */
 int32_t dqmc_global_update(dqmc_ctx* ctx, const int8_t* proposed, const double* uniforms, int32_t safe_mult,
                            int64_t* accepted, double* probs);
+/* running index of the next global update (checkpoint / resume of the counter RNG, like dqmc_set_sweep_index). */
+int32_t dqmc_set_global_update_index(dqmc_ctx* ctx, int64_t index);
 
 /* ---- results ------------------------------------------------------------------------------- */
 /* mc.stack.greens (effective Green's function), N x N x n_flavors per chain. */
@@ -161,9 +167,17 @@ int32_t dqmc_accumulate_greens(dqmc_ctx* ctx);
 /* Device pointer / element count of the accumulator block [count | sum | sumsq] so that the host
  * (torch.distributed / NCCL.jl) can all-reduce it in place over NVLink. */
 int32_t dqmc_observable_buffer(dqmc_ctx* ctx, void** device_ptr, int64_t* n_doubles);
-/* all-reduce (sum) of the accumulator block over an existing NCCL communicator (ncclComm_t);
- * NCCL is resolved at run time (dlopen libnccl.so.2), the communicator stays owned by the caller. */
+/* all-reduce (sum) of the accumulator blocks over an NCCL communicator, on the context's stream (ordered after the
+ * accumulation kernels).  nccl_comm: an existing ncclComm_t owned by the caller, or NULL for the communicator created
+ * by dqmc_comm_init.  NCCL is resolved at run time (dlopen libnccl.so.2). */
 int32_t dqmc_reduce_observables(dqmc_ctx* ctx, void* nccl_comm);
+/* A communicator owned by the context, for hosts without NCCL bindings of their own (the reference's parallel runs
+ * are one process per simulation, test/parallel.jl:62): rank 0 calls dqmc_comm_unique_id (ncclGetUniqueId, 128 bytes)
+ * and ships the bytes to every rank by any means (MPI.jl bcast, a file, torch.distributed); every rank then calls
+ * dqmc_comm_init (ncclCommInitRank on the context's device -- collective over the n_ranks contexts). */
+int32_t dqmc_comm_unique_id(uint8_t* id128);
+int32_t dqmc_comm_init(dqmc_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id128);
+int32_t dqmc_comm_destroy(dqmc_ctx* ctx);
 /* copy out: count, then mean and variance-of-the-mean inputs (sum, sumsq), N x N x n_flavors each. */
 int32_t dqmc_get_observables(dqmc_ctx* ctx, double* count, double* sum, double* sumsq);
 

@@ -27,7 +27,7 @@ class Desc(C.Structure):
                 ("hopping_exp_inv_squared", dp), ("hopping_exp", dp), ("hopping_exp_inv", dp),
                 ("check_sign_problem", C.c_int32), ("check_propagation_error", C.c_int32),
                 ("seed", C.c_uint64), ("chain_offset", C.c_int64), ("device", C.c_int32),
-                ("delay_block", C.c_int32)]
+                ("delay_block", C.c_int32), ("update_variant", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -85,6 +85,10 @@ def load():
         "dqmc_cgi_begin": (i32, [vp, i32, i32, i32, i32]),
         "dqmc_cgi_next": (i32, [vp, i32p, dp, dp, dp]),
         "dqmc_global_update": (i32, [vp, i8p, dp, i32, i64p, dp]),
+        "dqmc_set_global_update_index": (i32, [vp, i64]),
+        "dqmc_comm_unique_id": (i32, [u8p]),
+        "dqmc_comm_init": (i32, [vp, i32, i32, u8p]),
+        "dqmc_comm_destroy": (i32, [vp]),
         "dqmc_set_lattice": (i32, [vp, i32, i32, i32p, dp, C.c_double]),
         "dqmc_measurement_layout": (i32, [vp, i32p]),
         "dqmc_measure_equal_time": (i32, [vp]),

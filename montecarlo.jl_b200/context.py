@@ -38,7 +38,7 @@ class Context:
     def __init__(self, *, n_sites, n_slices, field_kind, n_chains, ranges, alpha,
                  hopping_exp_squared, hopping_exp_inv_squared, hopping_exp, hopping_exp_inv,
                  check_sign_problem=True, check_propagation_error=True, seed=1234, chain_offset=0,
-                 device=0, delay_block=0):
+                 device=0, delay_block=0, update_variant=0):
         self._L = _lib.load()
         self.N, self.M, self.kind, self.B = int(n_sites), int(n_slices), int(field_kind), int(n_chains)
         self.nb = 1 if self.kind == FIELD_DENSITY_HIRSCH else 2
@@ -57,6 +57,7 @@ class Context:
         d.hopping_exp, d.hopping_exp_inv = _dp(mats[2]), _dp(mats[3])
         d.check_sign_problem, d.check_propagation_error = int(check_sign_problem), int(check_propagation_error)
         d.seed, d.chain_offset, d.device, d.delay_block = int(seed), int(chain_offset), int(device), int(delay_block)
+        d.update_variant = int(update_variant)
         h = C.c_void_p()
         rc = self._L.dqmc_create(C.byref(d), C.byref(h))
         if rc != 0:
@@ -198,6 +199,27 @@ class Context:
 
     def set_sweep_index(self, s):
         self._ck(self._L.dqmc_set_sweep_index(self._h, int(s)))
+
+    def set_global_update_index(self, i):
+        self._ck(self._L.dqmc_set_global_update_index(self._h, int(i)))
+
+    # ------------------------------------------------------------------ NCCL communicator owned by the context
+    @staticmethod
+    def comm_unique_id():
+        """ncclGetUniqueId -> 128 bytes (rank 0; ship them to every rank)."""
+        buf = (C.c_uint8 * 128)()
+        rc = _lib.load().dqmc_comm_unique_id(buf)
+        if rc != 0:
+            raise DQMCError(f"dqmc_comm_unique_id failed ({rc}): {_lib.load().dqmc_last_error(None).decode()}")
+        return bytes(buf)
+
+    def comm_init(self, n_ranks, rank, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self._L.dqmc_comm_init(self._h, int(n_ranks), int(rank), buf))
+
+    def reduce_observables(self, comm=None):
+        """ncclAllReduce(sum) of the accumulator blocks on the context's stream (dqmc_reduce_observables)."""
+        self._ck(self._L.dqmc_reduce_observables(self._h, C.c_void_p(comm) if comm else None))
 
     # ------------------------------------------------------------------ results
     def _gshape(self, nchains):

@@ -19,7 +19,7 @@
 
 #include "ctx.cuh"
 
-namespace dqmc { long long g_kernel_launches = 0; }
+namespace dqmc { thread_local long long* t_launch_counter = nullptr; }
 
 static thread_local std::string g_create_error;
 
@@ -369,13 +369,15 @@ int32_t dqmc_max_sites(void) { return udt_max_n(); }
 
 const char* dqmc_last_error(const dqmc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-int64_t dqmc_kernel_launches(const dqmc_ctx*) { return g_kernel_launches; }
+int64_t dqmc_kernel_launches(const dqmc_ctx* c) { return c ? c->launches : 0; }
 
 int32_t dqmc_destroy(dqmc_ctx* c)
 {
     if (!c) return DQMC_OK;
     cudaSetDevice(c->device);
+    if (t_launch_counter == &c->launches) t_launch_counter = nullptr;
     if (c->st) cudaStreamSynchronize(c->st);
+    dqmc_comm_destroy(c);
     ut_destroy(c);
     meas_destroy(c);
     for (void* p : c->allocs) cudaFree(p);
@@ -428,11 +430,14 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     c->seed = d->seed; c->chain_offset = d->chain_offset; c->device = d->device;
     c->ld = (c->N + 1) & ~1; c->ms = (long long)c->ld * c->N; c->nmat = c->B * c->nb;
     c->ldv = ((c->N + 31) / 32) * 32;
-    // update3.cu (submatrix form) for n >= 96, update.cu (delayed rank-kb factors) below; DQMC_UPDATE_V1 / _V3 force
-    // one of them for A/B runs
+    // update3.cu (submatrix form) for n >= 96, update.cu (delayed rank-kb factors) below; desc.update_variant forces one
     // (measured: update3 wins from n = 144 up -- cfg 3 / 4 / 5 -- and loses at n = 64, where its per-block overheads
     // outweigh the saved flush passes: cfg 2 5195 vs 5970 sweeps/s)
-    c->update_version = getenv("DQMC_UPDATE_V1") ? 1 : (getenv("DQMC_UPDATE_V3") ? 3 : (c->N >= 96 ? 3 : 1));
+    if (d->update_variant != 0 && d->update_variant != 1 && d->update_variant != 3) {
+        delete c; g_create_error = "update_variant must be 0 (auto), 1 or 3"; return DQMC_ERR_INVALID;
+    }
+    c->update_version = d->update_variant ? d->update_variant : (c->N >= 96 ? 3 : 1);
+    t_launch_counter = &c->launches;
     if (c->update_version == 1) {
         c->kb = d->delay_block > 0 ? ((d->delay_block + 3) & ~3) : update_pick_kb(c->N, c->nb);
         const int kmax = update_pick_kb(c->N, c->nb);
@@ -782,7 +787,7 @@ int32_t dqmc_accumulate_greens(dqmc_ctx* c)
     const long long per = (long long)c->nb * c->ms;
     long long blocks = (per + 255) / 256; if (blocks > 592) blocks = 592;
     obs_accumulate_kernel<<<(unsigned)blocks, 256, 0, c->st>>>(c->greens_temp, per, c->B, c->obs, per);
-    ++g_kernel_launches;
+    count_launch();
     CK(c, cudaGetLastError());
     CK(c, cudaStreamSynchronize(c->st));
     return DQMC_OK;
@@ -795,26 +800,82 @@ int32_t dqmc_observable_buffer(dqmc_ctx* c, void** device_ptr, int64_t* n_double
     return DQMC_OK;
 }
 
+// ---- NCCL, resolved at run time (the library does not link libnccl) ---------------------------------------
+struct nccl_uid { char internal[128]; };                 // ncclUniqueId (nccl.h)
+struct NcclApi {
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(void**, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static const NcclApi& nccl_api()
+{
+    static const NcclApi api = [] {
+        NcclApi a;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return a;
+        a.GetUniqueId = (int (*)(nccl_uid*))dlsym(h, "ncclGetUniqueId");
+        a.CommInitRank = (int (*)(void**, int, nccl_uid, int))dlsym(h, "ncclCommInitRank");
+        a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+        a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+        a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce;
+        return a;
+    }();
+    return api;
+}
+
+int32_t dqmc_comm_unique_id(uint8_t* id128)
+{
+    if (!id128) { g_create_error = "dqmc_comm_unique_id: null argument"; return DQMC_ERR_INVALID; }
+    const NcclApi& n = nccl_api();
+    if (!n.ok) { g_create_error = "libnccl.so.2 not loadable"; return DQMC_ERR_UNSUPPORTED; }
+    nccl_uid u;
+    if (n.GetUniqueId(&u) != 0) { g_create_error = "ncclGetUniqueId failed"; return DQMC_ERR_CUDA; }
+    memcpy(id128, u.internal, 128);
+    return DQMC_OK;
+}
+
+int32_t dqmc_comm_init(dqmc_ctx* c, int32_t n_ranks, int32_t rank, const uint8_t* id128)
+{
+    ENTER(c);
+    if (!id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) FAIL(c, DQMC_ERR_INVALID, "dqmc_comm_init: bad arguments");
+    const NcclApi& n = nccl_api();
+    if (!n.ok) FAIL(c, DQMC_ERR_UNSUPPORTED, "dqmc_comm_init: libnccl.so.2 not loadable");
+    if (c->nccl_comm) { n.CommDestroy(c->nccl_comm); c->nccl_comm = nullptr; }
+    nccl_uid u;
+    memcpy(u.internal, id128, 128);
+    const int rc = n.CommInitRank(&c->nccl_comm, n_ranks, u, rank);
+    if (rc != 0) {
+        c->nccl_comm = nullptr;
+        FAIL(c, DQMC_ERR_CUDA, std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(rc) : "failed"));
+    }
+    return DQMC_OK;
+}
+
+int32_t dqmc_comm_destroy(dqmc_ctx* c)
+{
+    if (!c) return DQMC_ERR_INVALID;
+    if (c->nccl_comm) { nccl_api().CommDestroy(c->nccl_comm); c->nccl_comm = nullptr; }
+    return DQMC_OK;
+}
+
 int32_t dqmc_reduce_observables(dqmc_ctx* c, void* comm)
 {
     ENTER(c);
-    if (!comm) FAIL(c, DQMC_ERR_INVALID, "dqmc_reduce_observables: null communicator");
-    typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-    static allreduce_fn fn = nullptr;
-    if (!fn) {
-        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) FAIL(c, DQMC_ERR_UNSUPPORTED, "dqmc_reduce_observables: libnccl.so.2 not loadable");
-        fn = (allreduce_fn)dlsym(h, "ncclAllReduce");
-        if (!fn) FAIL(c, DQMC_ERR_UNSUPPORTED, "dqmc_reduce_observables: ncclAllReduce not found");
-    }
-    // ncclDouble = 8, ncclSum = 0 (nccl.h)
-    const int rc = fn(c->obs, c->obs, (size_t)c->obs_len, 8, 0, comm, c->st);
-    if (rc != 0) FAIL(c, DQMC_ERR_CUDA, "ncclAllReduce failed");
+    if (!comm) comm = c->nccl_comm;
+    if (!comm) FAIL(c, DQMC_ERR_INVALID, "dqmc_reduce_observables: no communicator (pass one or call dqmc_comm_init)");
+    const NcclApi& n = nccl_api();
+    if (!n.ok) FAIL(c, DQMC_ERR_UNSUPPORTED, "dqmc_reduce_observables: libnccl.so.2 not loadable");
+    // ncclDouble = 8, ncclSum = 0 (nccl.h); issued on the context's stream, i.e. ordered after the accumulation kernels
+    if (n.AllReduce(c->obs, c->obs, (size_t)c->obs_len, 8, 0, comm, c->st) != 0) FAIL(c, DQMC_ERR_CUDA, "ncclAllReduce failed");
     {   // the Wick-kernel accumulators of measure.cu ride along
         void* mptr = nullptr; int64_t mlen = 0;
         if (c->meas && dqmc_measurement_buffer(c, &mptr, &mlen) == DQMC_OK && mlen > 0)
-            if (fn(mptr, mptr, (size_t)mlen, 8, 0, comm, c->st) != 0) FAIL(c, DQMC_ERR_CUDA, "ncclAllReduce failed");
+            if (n.AllReduce(mptr, mptr, (size_t)mlen, 8, 0, comm, c->st) != 0) FAIL(c, DQMC_ERR_CUDA, "ncclAllReduce failed");
     }
     CK(c, cudaStreamSynchronize(c->st));
     return DQMC_OK;
@@ -842,6 +903,7 @@ static int32_t make_op_ctx(int device, int n, int batch, dqmc_ctx** out)
     if (n > udt_max_n()) { g_create_error = "n too large"; return DQMC_ERR_UNSUPPORTED; }
     cudaSetDevice(device);
     dqmc_ctx* c = new dqmc_ctx();
+    t_launch_counter = &c->launches;
     c->N = n; c->M = 1; c->nb = 1; c->B = batch; c->C = 1; c->device = device;
     c->ld = (n + 1) & ~1; c->ms = (long long)c->ld * n; c->nmat = batch; c->ldv = ((n + 31) / 32) * 32;
     cudaError_t e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);

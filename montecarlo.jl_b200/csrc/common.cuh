@@ -9,9 +9,33 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 namespace dqmc {
 
-extern long long g_kernel_launches;   // kernels launched by this library (instrumentation)
+// Kernel-launch counter of the context the calling thread is driving (set by the C ABI entry points; a context is
+// not thread-safe, but different threads may drive different contexts, so there is no process-wide counter).
+extern thread_local long long* t_launch_counter;
+inline void count_launch(int n = 1) { if (t_launch_counter) *t_launch_counter += n; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute (primary context): remember what has been
+// configured per device ordinal, so a second context on another GPU of the same process configures its own kernels.
+struct SmemAttr {
+    std::atomic<size_t> configured[64];
+    template <class K> cudaError_t ensure(K kern, size_t bytes)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        std::atomic<size_t>& slot = configured[dev & 63];
+        if (bytes <= slot.load(std::memory_order_acquire)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        size_t cur = slot.load(std::memory_order_relaxed);
+        while (cur < bytes && !slot.compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
+        return cudaSuccess;
+    }
+};
 
 // A diagonal factor fused into a kernel.  `field` mode evaluates
 // interaction_matrix_exp! (reference src/flavors/DQMC/fields.jl:380-386, 429-438)
@@ -52,7 +76,6 @@ struct GemmParams {
     Scale rs, ks, cs;
     const double* add_diag; long long add_stride;
     int batch;
-    int krep;            // 0 / 1 normally; > 1 repeats the k loop (timing experiments only)
 };
 
 cudaError_t launch_gemm(const GemmParams& p, cudaStream_t st);

@@ -31,7 +31,7 @@ struct dqmc_ctx {
     double *greens = nullptr, *greens_temp = nullptr, *Ul = nullptr, *Ur = nullptr, *Tl = nullptr, *Tr = nullptr;
     double *tmp1 = nullptr, *tmp2 = nullptr, *curr_U = nullptr, *Dl = nullptr, *Dr = nullptr;
     double* Dgreens = nullptr;         // D of the last Green's function calculation: det(greens) = 1 / prod(Dgreens)
-    int update_version = 3;            // 3: update3.cu (n >= 96), 1: update.cu; DQMC_UPDATE_V1 / DQMC_UPDATE_V3 force one
+    int update_version = 3;            // 3: update3.cu (n >= 96), 1: update.cu; dqmc_desc.update_variant forces one
     int8_t* conf_backup = nullptr;     // temp_conf of the global updates (fields.jl: temp_conf)
     double *Vwork = nullptr, *tau = nullptr, *udt_scratch = nullptr;
     int* pivot = nullptr; int* udt_iscratch = nullptr;
@@ -44,6 +44,9 @@ struct dqmc_ctx {
     // stack state (stack.jl:50-52)
     int current_slice = 0, current_range = 1, direction = 1;
     long long sweep_index = 0;
+    long long global_index = 0;        // running index of the global updates (site word of their counter-RNG uniform)
+    long long launches = 0;            // kernels launched on behalf of this context
+    void* nccl_comm = nullptr;         // communicator created by dqmc_comm_init (owned by the context)
     long long generation = 0;          // bumped whenever conf may have changed (mc.last_sweep's role for the ut stack)
     std::string err;
     std::vector<void*> allocs;
@@ -97,7 +100,8 @@ static inline double* slot_vec(dqmc_ctx* c, double* base, int slot) { return bas
 
 
 #define CE(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return e__; } while (0)
-#define ENTER(c) do { if (!(c)) return DQMC_ERR_INVALID; cudaSetDevice((c)->device); } while (0)
+#define ENTER(c) do { if (!(c)) return DQMC_ERR_INVALID; cudaSetDevice((c)->device); \
+    dqmc::t_launch_counter = &(c)->launches; } while (0)
 #define CHAINS_OK(c, c0, nc) ((c0) >= 0 && (nc) >= 0 && (c0) + (nc) <= (c)->B)
 
 // ---- building blocks defined in capi.cu ----------------------------------------------------------

@@ -12,7 +12,6 @@
 // staged with a 3-stage cp.async (LDGSTS) ring into padded shared memory laid out
 // so that every fragment load is bank-conflict free (leading dimension = 4 mod 16
 // doubles).  Roofline: FP64 pipe.
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace dqmc {
@@ -97,7 +96,6 @@ struct TileLoader {
         }
     }
     __device__ __forceinline__ void advance() { g += kstep; }
-    __device__ __forceinline__ void rewind(int ktiles) { g -= kstep * ktiles; }
 };
 
 template <int XT, bool KMAJOR, int BK>
@@ -138,8 +136,7 @@ gemm_kernel(const GemmParams p)
     const double* A = p.A + (long long)mat * p.strideA;
     const double* B = p.B + (long long)mat * p.strideB;
     double* C = p.C + (long long)mat * p.strideC;
-    const int KTr = (p.K + BK - 1) / BK;
-    const int KT = KTr * (p.krep > 0 ? p.krep : 1);   // krep > 1: timing experiment only (repeats the k loop)
+    const int KT = (p.K + BK - 1) / BK;
 
     // C read-modify-write without scalings (the panel updates of rdivp.cu):
     // the accumulators start from beta / alpha * C, so the loads of C overlap the main loop instead of sitting
@@ -169,7 +166,7 @@ gemm_kernel(const GemmParams p)
     TileLoader<BN, BKM, NT, BK> lb;
     la.init(A, p.lda, m0, p.M, tid);
     lb.init(B, p.ldb, n0, p.N, tid);
-    int kr_i = 0;                            // k-tile (mod KTr) the loaders point at
+    int kr_i = 0;                            // k-tile the loaders point at
     auto issue = [&](int stage) {
         const int k0 = kr_i * BK;
         la.issue(As + stage * AE, p.K - k0, tid);
@@ -179,7 +176,7 @@ gemm_kernel(const GemmParams p)
             const int gk = k0 + tid;
             Ks[stage * BK + tid] = (gk < p.K) ? scale_at(p.ks, mat, gk) : 0.0;
         }
-        if (++kr_i == KTr) { kr_i = 0; la.rewind(KTr); lb.rewind(KTr); }
+        ++kr_i;
     };
 
 #pragma unroll
@@ -251,15 +248,12 @@ static cudaError_t launch_cfg(const GemmParams& p, cudaStream_t st)
     constexpr int AE = tile_elems<BM, TA, BK>(), BE = tile_elems<BN, !TB, BK>();
     constexpr int smem = (STAGES * (AE + BE) + STAGES * BK) * (int)sizeof(double);
     auto kern = gemm_kernel<BM, BN, WM, WN, TA, TB, BK, STAGES, MINB>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static SmemAttr attr;
+    cudaError_t e = attr.ensure(kern, smem);
+    if (e != cudaSuccess) return e;
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, p.batch);
     kern<<<grid, NT, smem, st>>>(p);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -272,52 +266,18 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
         return mm * nn / ((double)p.M * (double)p.N);
     };
     const double w64 = waste(64, 64), w48 = waste(48, 48), w32 = waste(32, 32);
-    static const int variant = getenv("DQMC_GEMM_VARIANT") ? atoi(getenv("DQMC_GEMM_VARIANT")) : 0;
-    // (n = 288: a 96 x 96 CTA tile of nine 32 x 32 warp tiles covers it exactly like 48 x 48 does, but measured slower:
-    //  23.5 vs 25.4 TFLOP/s at 148 x 288^3)
-    if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) {
-        if (variant == 1 && p.M % 128 == 0) return launch_cfg<128, 64, 32, 32, TA, TB, 16, 3, 2>(p, st);
-        if (variant == 2) return launch_cfg<64, 64, 32, 32, TA, TB, 32, 3, 2>(p, st);
-        if (variant == 3) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4, 3>(p, st);
-        if (variant == 4 && p.M % 128 == 0) return launch_cfg<128, 64, 32, 32, TA, TB, 16, 4, 2>(p, st);
-        if (variant == 5) return launch_cfg<64, 64, 32, 16, TA, TB, 16, 3, 2>(p, st);
-        if (variant == 6) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 5>(p, st);
-        if (variant == 7) return launch_cfg<64, 64, 32, 16, TA, TB, 16, 2, 3>(p, st);
-        if (variant == 8) return launch_cfg<64, 64, 16, 32, TA, TB, 16, 3, 2>(p, st);
-        if (variant == 9) return launch_cfg<64, 64, 32, 16, TA, TB, 8, 4, 2>(p, st);
-        if (variant == 10) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 6>(p, st);
-        if (variant == 11) return launch_cfg<64, 64, 32, 32, TA, TB, 8, 3, 5>(p, st);
-        if (variant == 12) return launch_cfg<64, 64, 32, 32, TA, TB, 8, 4, 5>(p, st);
-        if (variant == 13) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 3, 4>(p, st);
-        if (variant == 20) return launch_cfg<64, 64, 32, 32, TA, TB, 32, 2, 3>(p, st);   // half the CTA barriers per tile
-        if (variant == 21) return launch_cfg<64, 64, 32, 32, TA, TB, 32, 2, 2>(p, st);
-        if (variant == 22) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 4>(p, st);
-        if (p.M % 128 == 0 && p.N % 128 == 0) {
-            if (variant == 14) return launch_cfg<128, 128, 32, 32, TA, TB, 16, 3, 1>(p, st);   // 16 warps, 1 CTA/SM: 8.0 waves
-            if (variant == 15) return launch_cfg<128, 128, 32, 32, TA, TB, 16, 4, 1>(p, st);
-            if (variant == 16) return launch_cfg<128, 128, 64, 32, TA, TB, 16, 3, 1>(p, st);   // 8 warps of 64 x 32
-            if (variant == 17) return launch_cfg<128, 128, 32, 64, TA, TB, 16, 3, 1>(p, st);   // 8 warps of 32 x 64
-            if (variant == 18) return launch_cfg<128, 64, 32, 32, TA, TB, 16, 3, 2>(p, st);    // 8 warps, 2 CTAs/SM: 8.0 waves
-            if (variant == 19) return launch_cfg<128, 128, 32, 32, TA, TB, 8, 4, 1>(p, st);
-        }
-        return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 5>(p, st);   // 2 stages, 5 CTAs/SM: best measured (28.7 TFLOP/s)
-    }
+    // Measured on 296 x 256^3 (profiles/r1_summary.md): 64 x 64 tiles, 2 stages, 5 CTAs/SM is the best of 22 variants
+    // (128 x 64 / 128 x 128 tiles, BK = 8 / 32, 3-4 stages were all slower: more co-resident CTAs at independent phases
+    // beat larger tiles); n = 288: a 96 x 96 CTA tile covers it exactly like 48 x 48 does but measured slower.
+    if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9)
+        return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 5>(p, st);
     if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
     return launch_cfg<32, 32, 16, 16, TA, TB>(p, st);
 }
 
-static cudaError_t launch_gemm_impl(const GemmParams& p, cudaStream_t st);
-
 cudaError_t launch_gemm(const GemmParams& p, cudaStream_t st)
 {
     if (p.batch <= 0 || p.M <= 0 || p.N <= 0) return cudaSuccess;
-    static const int krep = getenv("DQMC_GEMM_KREP") ? atoi(getenv("DQMC_GEMM_KREP")) : 0;
-    if (krep > 0) { GemmParams q = p; q.krep = krep; return launch_gemm_impl(q, st); }
-    return launch_gemm_impl(p, st);
-}
-
-static cudaError_t launch_gemm_impl(const GemmParams& p, cudaStream_t st)
-{
     if ((p.lda & 1) || (p.ldb & 1)) return cudaErrorInvalidValue;   // 16-byte cp.async columns
     if (!p.transA && !p.transB) return launch_tiles<false, false>(p, st);
     if (!p.transA && p.transB) return launch_tiles<false, true>(p, st);

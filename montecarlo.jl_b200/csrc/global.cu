@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256)
 global_decide_kernel(const double* __restrict__ Dold, const double* __restrict__ Dnew, const int8_t* __restrict__ conf_new,
                      const int8_t* __restrict__ conf_old, int N, int M, int nb, int kind, double alpha,
                      const double* __restrict__ uniforms, unsigned long long seed, long long chain0, long long sweep,
-                     int* accept, double* probs)
+                     unsigned int global_index, int* accept, double* probs)
 {
     const int chain = blockIdx.x;
     __shared__ long long red[8];
@@ -48,7 +48,7 @@ global_decide_kernel(const double* __restrict__ Dold, const double* __restrict__
         const double dE = (kind == 0) ? alpha * (double)tot : 0.0;
         const double p = fabs(exp(-dE) * detratio);
         const double u = uniforms ? uniforms[chain]
-                                  : dqmc_uniform(seed, (uint64_t)(chain0 + chain), (uint64_t)sweep, (uint32_t)(2 * M), 0u);
+                                  : dqmc_uniform(seed, (uint64_t)(chain0 + chain), (uint64_t)sweep, (uint32_t)(2 * M), global_index);
         accept[chain] = (p > 1.0 || u < p) ? 1 : 0;
         if (probs) probs[chain] = p;
     }
@@ -75,45 +75,69 @@ extern "C" int32_t dqmc_global_update(dqmc_ctx* c, const int8_t* proposed, const
             if (proposed[i] != 1 && proposed[i] != -1) FAIL(c, DQMC_ERR_INVALID, "dqmc_global_update: conf values must be +-1");
     if (!c->conf_backup) CK(c, dalloc(c, &c->conf_backup, tot));
     int* d_acc = nullptr; double* d_p = nullptr; double* d_u = nullptr;
-    CK(c, cudaMallocAsync((void**)&d_acc, (size_t)c->B * sizeof(int), c->st));
-    CK(c, cudaMallocAsync((void**)&d_p, (size_t)c->B * sizeof(double), c->st));
+    bool conf_replaced = false;
+    // every exit path frees the temporaries; a failure after propose_conf! puts the old configuration back
+    auto cleanup = [&](bool failed) {
+        if (failed && conf_replaced) cudaMemcpyAsync(c->conf, c->conf_backup, tot, cudaMemcpyDeviceToDevice, c->st);
+        if (d_acc) cudaFreeAsync(d_acc, c->st);
+        if (d_p) cudaFreeAsync(d_p, c->st);
+        if (d_u) cudaFreeAsync(d_u, c->st);
+        if (failed) cudaStreamSynchronize(c->st);
+    };
+#define GCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(true); \
+    c->err = std::string(#call) + ": " + cudaGetErrorString(e__); return DQMC_ERR_CUDA; } } while (0)
+    GCK(cudaMallocAsync((void**)&d_acc, (size_t)c->B * sizeof(int), c->st));
+    GCK(cudaMallocAsync((void**)&d_p, (size_t)c->B * sizeof(double), c->st));
     if (uniforms) {
-        CK(c, cudaMallocAsync((void**)&d_u, (size_t)c->B * sizeof(double), c->st));
-        CK(c, cudaMemcpyAsync(d_u, uniforms, (size_t)c->B * 8, cudaMemcpyHostToDevice, c->st));
+        GCK(cudaMallocAsync((void**)&d_u, (size_t)c->B * sizeof(double), c->st));
+        GCK(cudaMemcpyAsync(d_u, uniforms, (size_t)c->B * 8, cudaMemcpyHostToDevice, c->st));
     }
     // propose_conf!: temp_conf <- conf, conf <- proposal
-    CK(c, cudaMemcpyAsync(c->conf_backup, c->conf, tot, cudaMemcpyDeviceToDevice, c->st));
-    if (proposed) CK(c, cudaMemcpyAsync(c->conf, proposed, tot, cudaMemcpyHostToDevice, c->st));
+    GCK(cudaMemcpyAsync(c->conf_backup, c->conf, tot, cudaMemcpyDeviceToDevice, c->st));
+    conf_replaced = true;
+    if (proposed) GCK(cudaMemcpyAsync(c->conf, proposed, tot, cudaMemcpyHostToDevice, c->st));
     else {
         flip_conf_kernel<<<592, 256, 0, c->st>>>(c->conf, (long long)tot);
-        ++g_kernel_launches;
-        CK(c, cudaGetLastError());
+        ++c->launches;
+        GCK(cudaGetLastError());
     }
     c->generation += 1;
     // inv_det(mc, current_slice - 1 = 0, field): (Ur Dr Tr)' = B_M ... B_1, Ul Dl Tl = identity
-    CK(c, build_chain_udt(c, 0, safe_mult, true, c->Ur, c->Dr, c->Tr));
-    CK(c, load_udt(c, c->Ul, c->Dl, c->Tl, -1));
-    CK(c, calculate_inv_greens_udt(c, c->greens_temp));
+    GCK(build_chain_udt(c, 0, safe_mult, true, c->Ur, c->Dr, c->Tr));
+    GCK(load_udt(c, c->Ul, c->Dl, c->Tl, -1));
+    GCK(calculate_inv_greens_udt(c, c->greens_temp));
     {
         ProfScope ps(c, DQMC_PROF_OTHER);
+        // the counter-RNG uniform of a global update is keyed by (chain, sweep index, step = 2M, site = running index of
+        // the global update): consecutive global updates without a local sweep in between draw different uniforms
         global_decide_kernel<<<(unsigned)c->B, 256, 0, c->st>>>(c->Dgreens, c->Dr, c->conf, c->conf_backup, c->N, c->M, c->nb,
                                                                 c->kind, c->alpha, d_u, c->seed, c->chain_offset,
-                                                                c->sweep_index, d_acc, d_p);
-        ++g_kernel_launches;
-        CK(c, cudaGetLastError());
+                                                                c->sweep_index, (unsigned int)c->global_index, d_acc, d_p);
+        ++c->launches;
+        GCK(cudaGetLastError());
         dim3 grid(16, (unsigned)c->B);
         restore_conf_kernel<<<grid, 256, 0, c->st>>>(c->conf, c->conf_backup, d_acc, (long long)per);
-        ++g_kernel_launches;
-        CK(c, cudaGetLastError());
+        ++c->launches;
+        GCK(cudaGetLastError());
     }
+    c->global_index += 1;
+    conf_replaced = false;                               // from here on conf is consistent (accepted or restored per chain)
     // accept_global!: full rebuild (rejected chains rebuild their old configuration)
-    CK(c, reverse_build(c));
-    CK(c, propagate(c));
+    GCK(reverse_build(c));
+    GCK(propagate(c));
     std::vector<int> h((size_t)c->B);
-    CK(c, cudaMemcpyAsync(h.data(), d_acc, (size_t)c->B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    if (probs) CK(c, cudaMemcpyAsync(probs, d_p, (size_t)c->B * 8, cudaMemcpyDeviceToHost, c->st));
-    CK(c, cudaStreamSynchronize(c->st));
+    GCK(cudaMemcpyAsync(h.data(), d_acc, (size_t)c->B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    if (probs) GCK(cudaMemcpyAsync(probs, d_p, (size_t)c->B * 8, cudaMemcpyDeviceToHost, c->st));
+    GCK(cudaStreamSynchronize(c->st));
     if (accepted) for (int b = 0; b < c->B; ++b) accepted[b] = h[b];
-    cudaFreeAsync(d_acc, c->st); cudaFreeAsync(d_p, c->st); if (d_u) cudaFreeAsync(d_u, c->st);
+    cleanup(false);
+#undef GCK
+    return DQMC_OK;
+}
+
+extern "C" int32_t dqmc_set_global_update_index(dqmc_ctx* c, int64_t i)
+{
+    if (!c || i < 0) return DQMC_ERR_INVALID;
+    c->global_index = i;
     return DQMC_OK;
 }

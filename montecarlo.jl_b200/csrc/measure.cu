@@ -153,14 +153,14 @@ static cudaError_t launch_pair(dqmc_ctx* c, const double* G00, const double* G0l
     pair_obs_kernel<<<grid, 256, (size_t)4 * m->nbr * sizeof(double), c->st>>>(
         G00, G0l, Gl0, Gll, l_is_zero, weight, m->s2d, m->nbr, m->nbasis, c->N, c->ld, c->ms, c->nb, m->res,
         m->off[OBS_COUNT], o_cd, o_cd + per, o_cd + 2 * per, o_cd + 3 * per);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 static cudaError_t launch_zero(dqmc_ctx* c, int o0, int o1)
 {
     dqmc_meas* m = c->meas;
     meas_zero_kernel<<<148, 256, 0, c->st>>>(m->res, m->off[OBS_COUNT], o0, o1, c->B);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 static cudaError_t launch_commit(dqmc_ctx* c, int o0, int o1, int which_count)
@@ -169,7 +169,7 @@ static cudaError_t launch_commit(dqmc_ctx* c, int o0, int o1, int which_count)
     const int blocks = std::min(148, (o1 - o0 + 255) / 256);
     meas_commit_kernel<<<blocks, 256, 0, c->st>>>(m->res, m->off[OBS_COUNT], o0, o1, c->B, m->acc, which_count,
                                                   m->off[OBS_COUNT]);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -238,7 +238,7 @@ int32_t dqmc_measure_equal_time(dqmc_ctx* c)
         scalar_obs_kernel<<<(unsigned)c->B, 256, 0, c->st>>>(c->greens_temp, m->thop, m->U, c->N, c->ld, c->ms, c->nb,
                                                               m->res, m->off[OBS_COUNT], m->off[OBS_OCC], m->off[OBS_K],
                                                               m->off[OBS_V], m->off[OBS_E]);
-        ++g_kernel_launches;
+        count_launch();
         CK(c, cudaGetLastError());
     }
     CK(c, launch_pair(c, c->greens_temp, c->greens_temp, c->greens_temp, c->greens_temp, 1, 1.0, m->off[OBS_CDC]));

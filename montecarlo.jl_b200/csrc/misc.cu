@@ -21,7 +21,7 @@ cudaError_t launch_set_identity(double* A, int n, int ld, long long stride, int 
     const long long tot = (long long)ld * n;
     dim3 grid((unsigned)((tot + 255) / 256 > 64 ? 64 : (tot + 255) / 256), (unsigned)batch);
     set_identity_kernel<<<grid, 256, 0, st>>>(A, n, ld, stride);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -36,7 +36,7 @@ cudaError_t launch_fill(double* v, double val, long long count, cudaStream_t st)
     if (count <= 0) return cudaSuccess;
     long long b = (count + 255) / 256; if (b > 1184) b = 1184;
     fill_kernel<<<(unsigned)b, 256, 0, st>>>(v, val, count);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -60,14 +60,14 @@ cudaError_t launch_permute_cols(const double* A, double* O, const int* pivot, in
     if (batch <= 0) return cudaSuccess;
     dim3 grid((unsigned)(n < 32 ? n : 32), (unsigned)batch);
     permute_cols_kernel<<<grid, 128, 0, st>>>(A, O, pivot, n, ld, stride, pstride);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 
 // Propagation-error check (reference stack.jl:644-654, 699-709): d = max|A - B| over the
 // chain's matrices; if d > thresh push into MagnitudeStats [count, sum log10, min, max].
 __global__ void prop_error_kernel(const double* A, const double* B, int n, int ld, long long stride_chain,
-                                  int nb, double thresh, double* stats)
+                                  int nb, double thresh, double* stats, int s)
 {
     const int chain = blockIdx.x;
     const double* a = A + (long long)chain * stride_chain;
@@ -76,9 +76,11 @@ __global__ void prop_error_kernel(const double* A, const double* B, int n, int l
     // flight for one SM's share of HBM bandwidth
     double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
     const int cols = nb * n;
-    for (int i = threadIdx.x % ld; i < n; i += ld)                   // at most one pass: threads own a row, walk columns
-        for (int j = threadIdx.x / ld; j < cols; j += 4 * (blockDim.x / ld)) {
-            const int s = blockDim.x / ld;
+    // s * ld threads own (row, column group); the block is rounded up to whole warps and the extra threads only take
+    // part in the reduction (with m = 0)
+    const bool active = (int)threadIdx.x < s * ld;
+    for (int i = active ? (int)threadIdx.x % ld : n; i < n; i += ld)   // at most one pass: threads own a row, walk columns
+        for (int j = threadIdx.x / ld; j < cols; j += 4 * s) {
             const long long e0 = (long long)j * ld + i;
             const bool p1 = j + s < cols, p2 = j + 2 * s < cols, p3 = j + 3 * s < cols;
             const double a0 = a[e0], b0 = b[e0];
@@ -108,12 +110,13 @@ cudaError_t launch_prop_error(const double* A, const double* B, int n, int ld, l
 {
     if (n_chains <= 0) return cudaSuccess;
     // threads = a multiple of ld so that every thread owns one row (rows >= n are padding and idle)
-    int threads = (1024 / ld) * ld;
-    if (threads == 0) {   // ld > 1024 does not occur (n <= 512); keep the kernel's ownership rule valid anyway
+    const int s = 1024 / ld;
+    if (s == 0) {   // ld > 1024 does not occur (n <= 512); keep the kernel's ownership rule valid anyway
         return cudaErrorInvalidValue;
     }
-    prop_error_kernel<<<(unsigned)n_chains, threads, 0, st>>>(A, B, n, ld, stride_chain, nb, thresh, stats);
-    ++g_kernel_launches;
+    const int threads = ((s * ld + 31) / 32) * 32;       // whole warps: the shuffle reduction needs full masks
+    prop_error_kernel<<<(unsigned)n_chains, threads, 0, st>>>(A, B, n, ld, stride_chain, nb, thresh, stats, s);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -132,7 +135,7 @@ cudaError_t launch_accumulate(const double* G, double* sum, double* sumsq, long 
     if (count <= 0) return cudaSuccess;
     long long b = (count + 255) / 256; if (b > 1184) b = 1184;
     accumulate_kernel<<<(unsigned)b, 256, 0, st>>>(G, sum, sumsq, count);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -167,7 +170,7 @@ cudaError_t launch_scale_add(double* O, const double* A, Scale rs, Scale cs, con
     const long long tot = (long long)ld * n;
     dim3 grid((unsigned)((tot + 255) / 256 > 64 ? 64 : (tot + 255) / 256), (unsigned)batch);
     scale_add_kernel<<<grid, 256, 0, st>>>(O, A, rs, cs, add, add_diag, n, ld, stride);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -199,7 +202,7 @@ cudaError_t launch_conf_bits(int8_t* conf, unsigned long long* chunks, long long
     const long long wpc = (nbits + 63) / 64, tot = wpc * n_chains;
     long long b = (tot + 255) / 256; if (b > 1184) b = 1184;
     conf_bits_kernel<<<(unsigned)b, 256, 0, st>>>(conf, chunks, nbits, wpc, n_chains, pack);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -68,7 +68,7 @@ cudaError_t launch_rdivp(const RdivpParams& p, cudaStream_t st)
         dim3 grid((unsigned)((p.n + 127) / 128), (unsigned)p.batch);
         trsm_diag_kernel<<<grid, 128, 0, st>>>(p.A, p.work, p.T, p.n, p.ld, j0, jb, p.strideA, p.strideT,
                                                p.strideW);
-        ++g_kernel_launches;
+        count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

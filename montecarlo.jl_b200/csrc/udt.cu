@@ -22,7 +22,6 @@
 // Q is then accumulated backwards over the same resident layout.
 // Roofline: shared-memory bandwidth / FP64 FMA (level-2 work), see DESIGN.md.
 #include <cooperative_groups.h>
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -301,16 +300,12 @@ cudaError_t launch_udt(const UdtParams& p, cudaStream_t st)
 {
     if (p.batch <= 0) return cudaSuccess;
     // v2: register-resident panel (udt_reg.cu); v1 (shared-memory panel, below) covers larger n
-    static const bool force_v1 = getenv("DQMC_UDT_V1") != nullptr;
-    if (!force_v1 && udt_reg_supported(p.n)) return launch_udt_reg(p, st);
+    if (udt_reg_supported(p.n)) return launch_udt_reg(p, st);
     const UdtGeom g = udt_geometry(p.n);
     if (g.smem > 220 * 1024) return cudaErrorInvalidConfiguration;
-    static size_t configured = 0;
-    if (g.smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(udt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-        if (e != cudaSuccess) return e;
-        configured = g.smem;
-    }
+    static SmemAttr attr;
+    cudaError_t e = attr.ensure(udt_kernel, g.smem);
+    if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.batch * g.cs));
     cfg.blockDim = dim3((unsigned)g.nt);
@@ -320,7 +315,7 @@ cudaError_t launch_udt(const UdtParams& p, cudaStream_t st)
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)g.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    ++g_kernel_launches;
+    count_launch();
     return cudaLaunchKernelEx(&cfg, udt_kernel, p, g);
 }
 

@@ -28,7 +28,6 @@
 //
 // Bound: latency of the per-step critical path; FP64 FMA pipe ~13 % busy (profiles/r1_summary.md).
 #include <cooperative_groups.h>
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -55,8 +54,7 @@ static bool udt_level_geometry(int n, UdtLevel& g)
     const int rpl = (n + 31) / 32;
     if (rpl > 9) return false;
     const int maxw = (rpl <= 4) ? 16 : ((rpl <= 6) ? 12 : 8);  // matches the __launch_bounds__ below
-    static const int min_cs = getenv("DQMC_UDT_CS") ? atoi(getenv("DQMC_UDT_CS")) : 1;   // experiment knob
-    for (int cs = min_cs; cs <= 8; cs *= 2) {
+    for (int cs = 1; cs <= 8; cs *= 2) {
         const int nloc = (n + cs - 1) / cs;
         const int w = (nloc + 7) / 8;
         if (w <= maxw) {
@@ -489,70 +487,6 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
 }
 
 // ================================================================================================
-// explicit Q = H_0 ... H_{n-1} I, backwards (UDT.jl:272-288).  One CTA = 64 columns, warps independent.
-// ================================================================================================
-template <int RPL>
-__global__ void __launch_bounds__(256)
-udt_formq_kernel(const UdtParams p, int cols_per_cta)
-{
-    const int n = p.n, ld = p.ld, ldv = p.ldv;
-    const int ctas_per_mat = (n + cols_per_cta - 1) / cols_per_cta;
-    const int mat = blockIdx.x / ctas_per_mat, part_i = blockIdx.x - mat * ctas_per_mat;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int col0 = part_i * cols_per_cta + warp * 8;   // this warp owns columns col0 .. col0 + 7
-    if (col0 >= n) return;
-    const double* Vg = p.Vwork + (long long)mat * p.strideV;
-    const double* tg = p.tau + (long long)mat * p.strideTau;
-    double* Ug = p.U + (long long)mat * p.strideU;
-
-    double a[8][RPL], part[8];
-    int cmax = -1;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int col = col0 + c;
-        if (col < n) cmax = col;
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) a[c][r] = (col < n && lane + 32 * r == col) ? 1.0 : 0.0;
-    }
-    // reflector k only touches columns >= k, so this warp starts at k = cmax
-    double vn[RPL], taun;
-    auto load_v = [&](int k, double (&dst)[RPL], double& t) {   // V columns are stored complete (0 .. 0 1 v)
-        const int kk = k < 0 ? 0 : k;
-        const double* src = Vg + (long long)kk * ldv + lane;
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) dst[r] = src[32 * r];
-        t = tg[kk];
-    };
-    load_v(cmax, vn, taun);
-    for (int k = cmax; k >= 0; --k) {
-        double v[RPL];
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) v[r] = vn[r];
-        const double tau = taun;
-        load_v(k - 1, vn, taun);                         // prefetch the next vector from L2
-        const int r0 = k >> 5;
-        unsigned m = 0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            if (col0 + c < n && col0 + c >= k) m |= 1u << c;
-        col_dots<RPL>(a, v, m, part, r0);
-        warp_allreduce8(part, lane);
-        col_update<RPL, false>(a, v, part, tau, 0ull, r0);
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int col = col0 + c;
-        if (col < n) {
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) {
-                const int row = lane + 32 * r;
-                if (row < n) Ug[row + (long long)col * ld] = a[c][r];
-            }
-        }
-    }
-}
-
-// ================================================================================================
 // explicit Q, blocked: four reflectors at a time in compact WY form,
 //     H_k H_{k+1} H_{k+2} H_{k+3} = I - V T V^T   (T 4 x 4 upper triangular, LAPACK dlarft "forward, columnwise").
 // The per-reflector kernel above is bound by its dependent chain (dots -> shuffle tree -> update) once per
@@ -767,140 +701,6 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
 #undef TS
 
 // ================================================================================================
-// explicit Q, blocked, with Q held in the DMMA accumulator layout: thread (g, t) of a warp owns rows 8 i + g and the
-// two columns 2 t, 2 t + 1 of the warp's 8 columns.  Per block of four reflectors the dot products W = V^T Q are
-// thread-local over the owned rows (8 chains), reduced over g with a 3-round butterfly; Y = T W; and the update
-// Q -= V Y is ONE m8n8k4 DMMA per 8 rows (A = V rows from shared memory, B = -Y) instead of 64 DFMAs.  ~580
-// instructions per block and warp instead of ~1250: the kernel runs at the FP64 pipe.
-// ================================================================================================
-__device__ __forceinline__ void dmma884q(double& c0, double& c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-template <int RPL>
-__global__ void __launch_bounds__(256)
-udt_formq5_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
-{
-    constexpr int NV = RPL * 32, RT = RPL * 4, CH = 4;
-    const int n = p.n, ld = p.ld, ldv = p.ldv;
-    const int ctas_per_mat = (n + 63) / 64;
-    const int mat = blockIdx.x / ctas_per_mat, part_i = blockIdx.x - mat * ctas_per_mat;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g8 = lane >> 2, t4 = lane & 3;
-    const int col0 = part_i * 64 + warp * 8;             // this warp owns columns col0 .. col0 + 7
-    const double* Vg = p.Vwork + (long long)mat * p.strideV;
-    const double* Tg = T4 + (long long)mat * ngroups * 16;
-    double* Ug = p.U + (long long)mat * p.strideU;
-
-    extern __shared__ __align__(16) double fq_sm[];
-    double* vsb = fq_sm;                                 // [2][CH * 4][NV]
-    double* tsb = fq_sm + (size_t)2 * CH * 4 * NV;       // [2][CH][16]
-#define VS(s_, jj_, r_) vsb[((size_t)(s_) * CH * 4 + (jj_)) * NV + (r_)]
-#define TS(s_, gb_, i_) tsb[((s_) * CH + (gb_)) * 16 + (i_)]
-
-    double q[RT][2];
-#pragma unroll
-    for (int i = 0; i < RT; ++i)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) q[i][e] = (col0 + 2 * t4 + e < n && 8 * i + g8 == col0 + 2 * t4 + e) ? 1.0 : 0.0;
-
-    const int ctop = min(n, part_i * 64 + 64) - 1;       // highest column of this CTA
-    const int gtop = ctop >> 2;
-    const int wtop = (col0 < n) ? (min(n - 1, col0 + 7) >> 2) : -1;   // highest block that touches this warp
-    const bool dense = (ldv == NV);
-    auto stage = [&](int cidx, int s) {                  // blocks CH cidx .. CH cidx + CH - 1 -> stage s
-        for (int e = tid; e < CH * 4 * (NV / 2); e += 256) {
-            const int jj = e / (NV / 2), r2 = (e - jj * (NV / 2)) * 2;
-            const int k = CH * 4 * cidx + jj;
-            if (k < n && (dense || r2 + 1 < ldv)) cp_async16_q(&VS(s, jj, r2), Vg + (long long)k * ldv + r2);
-            else { VS(s, jj, r2) = 0.0; VS(s, jj, r2 + 1) = 0.0; }
-        }
-        if (tid < CH * 16) {
-            const int g = CH * cidx + (tid >> 4);
-            TS(s, tid >> 4, tid & 15) = (g < ngroups) ? Tg[(long long)g * 16 + (tid & 15)] : 0.0;
-        }
-        asm volatile("cp.async.commit_group;\n" ::);
-    };
-
-    const int ctopc = gtop / CH;
-    stage(ctopc, 0);
-    for (int cidx = ctopc; cidx >= 0; --cidx) {
-        const int s = (ctopc - cidx) & 1;
-        asm volatile("cp.async.wait_group 0;\n" ::);
-        __syncthreads();                                 // chunk visible; everybody is done with the previous one
-        if (cidx > 0) stage(cidx - 1, s ^ 1);
-        for (int gb = CH - 1; gb >= 0; --gb) {
-            const int g = CH * cidx + gb;
-            if (g > gtop || g > wtop) continue;          // warp-uniform
-            const int i0 = (4 * g) >> 3;                 // first 8-row tile a reflector of this block touches
-            // ---- W = V^T Q, thread-local over the owned rows --------------------------------------------
-            double w[4][2];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) w[j][0] = w[j][1] = 0.0;
-#pragma unroll
-            for (int i = 0; i < RT; ++i)
-                if (i >= i0) {                           // warp-uniform
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double v = VS(s, gb * 4 + j, 8 * i + g8);
-                        w[j][0] = fma(v, q[i][0], w[j][0]);
-                        w[j][1] = fma(v, q[i][1], w[j][1]);
-                    }
-                }
-            // ---- butterfly over g (lanes 4 g + t): every lane ends with the complete W[:, 2 t .. 2 t + 1] -----------
-#pragma unroll
-            for (int o = 4; o <= 16; o <<= 1)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    w[j][0] += __shfl_xor_sync(0xffffffffu, w[j][0], o);
-                    w[j][1] += __shfl_xor_sync(0xffffffffu, w[j][1], o);
-                }
-            // ---- Y = T W (T upper triangular) ---------------------------------------------------------------
-            double y[4][2];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                for (int i = j; i < 4; ++i) {
-                    const double tv = TS(s, gb, j + 4 * i);
-                    a0 = fma(tv, w[i][0], a0); a1 = fma(tv, w[i][1], a1);
-                }
-                y[j][0] = a0; y[j][1] = a1;
-            }
-            // ---- B operand of the update: -Y[j = t][column g]: columns 2 t', 2 t' + 1 live in the lanes with t' = g >> 1 ------
-            double yb = 0.0;
-            {
-                const int src = g8 >> 1;                 // lane (g' = 0, t' = g >> 1)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double v0 = __shfl_sync(0xffffffffu, y[j][0], src);
-                    const double v1 = __shfl_sync(0xffffffffu, y[j][1], src);
-                    if (j == t4) yb = (g8 & 1) ? v1 : v0;
-                }
-                yb = -yb;
-            }
-            // ---- Q -= V Y: one DMMA per 8 rows ----------------------------------------------------------------
-#pragma unroll
-            for (int i = 0; i < RT; ++i)
-                if (i >= i0) dmma884q(q[i][0], q[i][1], VS(s, gb * 4 + t4, 8 * i + g8), yb);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < RT; ++i) {
-        const int row = 8 * i + g8;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int col = col0 + 2 * t4 + e;
-            if (row < n && col < n) Ug[row + (long long)col * ld] = q[i][e];
-        }
-    }
-#undef VS
-#undef TS
-}
-
-// ================================================================================================
 // host side
 // ================================================================================================
 template <int RPL>
@@ -915,7 +715,7 @@ static cudaError_t launch_steps(const UdtParams& p, const UdtLevel& g, cudaStrea
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)g.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    ++g_kernel_launches;
+    count_launch();
     return cudaLaunchKernelEx(&cfg, udt_steps_kernel<RPL>, p, g);
 }
 
@@ -924,35 +724,19 @@ static cudaError_t launch_formq4(const UdtParams& p, double* T4, cudaStream_t st
 {
     const int ngroups = (p.n + 3) / 4;
     const int warps = p.batch * ngroups;
-    ++g_kernel_launches;
+    count_launch();
     udt_wy_t_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(p, T4, ngroups);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int ctas = p.batch * ((p.n + 63) / 64);
-    ++g_kernel_launches;
+    count_launch();
     constexpr int smem = (2 * 4 * 4 * RPL * 32 + 2 * 4 * 16) * (int)sizeof(double);
-    // A/B knob: Q in the DMMA accumulator layout (udt_formq5_kernel) measured SLOWER (1.38 vs 0.96 ms per 296 x 256^2)
-    static const bool v4 = getenv("DQMC_UDT_FORMQ_V5") == nullptr;
-    static bool attr_done = false;
-    if (!attr_done) {
-        e = cudaFuncSetAttribute(udt_formq4_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(udt_formq5_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    if (v4) udt_formq4_kernel<RPL><<<(unsigned)ctas, 256, smem, st>>>(p, T4, ngroups);
-    else udt_formq5_kernel<RPL><<<(unsigned)ctas, 256, smem, st>>>(p, T4, ngroups);
-    return cudaGetLastError();
-}
-
-template <int RPL>
-static cudaError_t launch_formq(const UdtParams& p, cudaStream_t st)
-{
-    const int cols_per_cta = 64;
-    const int ctas = p.batch * ((p.n + cols_per_cta - 1) / cols_per_cta);
-    ++g_kernel_launches;
-    udt_formq_kernel<RPL><<<(unsigned)ctas, 256, 0, st>>>(p, cols_per_cta);
+    // (Q held in the DMMA accumulator layout with the update as one DMMA per 8 rows was measured SLOWER: 1.38 vs
+    //  0.96 ms per 296 x 256^2 -- see DESIGN.md; it is not part of the build)
+    static SmemAttr attr;
+    e = attr.ensure(udt_formq4_kernel<RPL>, smem);
+    if (e != cudaSuccess) return e;
+    udt_formq4_kernel<RPL><<<(unsigned)ctas, 256, smem, st>>>(p, T4, ngroups);
     return cudaGetLastError();
 }
 
@@ -971,8 +755,7 @@ bool udt_reg_supported(int n) { UdtLevel g{}; return udt_level_geometry(n, g); }
 // of the trailing block the level that starts with nk columns hands on (0: it finishes the factorisation).
 static int udt_next_level_size(int nk)
 {
-    static const bool one_level = getenv("DQMC_UDT_ONE_LEVEL") != nullptr;   // A/B knob
-    if (one_level || nk <= 64) return 0;
+    if (nk <= 64) return 0;
     static const int sizes[4] = {256, 192, 128, 64};
     for (int k = 0; k < 4; ++k)
         if (sizes[k] < nk) return sizes[k];
@@ -1029,10 +812,8 @@ cudaError_t launch_udt_reg(const UdtParams& p, cudaStream_t st)
     }
     // Q
     const int rpl = (n + 31) / 32;
-    static const bool formq_v1 = getenv("DQMC_UDT_FORMQ_V1") != nullptr;     // A/B knob: per-reflector kernel
     double* T4 = S_base + s_off;                         // behind the trailing-block buffers
-    if (formq_v1) { DQMC_RPL_SWITCH(rpl, (launch_formq<R>(p, st))) }
-    else { DQMC_RPL_SWITCH(rpl, (launch_formq4<R>(p, T4, st))) }
+    DQMC_RPL_SWITCH(rpl, (launch_formq4<R>(p, T4, st)))
     if (err != cudaSuccess) return err;
     // the Val(false) form wants the columns of D^-1 R in pivot (logical) order
     if (!direct_T)

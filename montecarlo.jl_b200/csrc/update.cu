@@ -21,7 +21,6 @@
 #include "common.cuh"
 #include "../../include/dqmc_rng.h"
 #include <math.h>
-#include <stdlib.h>
 
 namespace dqmc {
 
@@ -72,18 +71,13 @@ struct UpdShared {
     double gdiag[2][32];     // current G_ii of the sites of the block, per flavor (kb <= 32)
 };
 
-#define UPD_TICK(slot) do { if (dbg) { const long long t__ = clock64(); dacc[slot] += t__ - tprev; tprev = t__; } } while (0)
 
-__global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const int ldu, const double em2a, const double ep2a,
-                                                      long long* dbg_all)
+__global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const int ldu, const double em2a, const double ep2a)
 {
     extern __shared__ __align__(16) double sm[];
     const int n = p.n, nb = p.nb, kb = p.kb, ld = p.ld;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
     const int chain = blockIdx.x;
-    long long* dbg = (blockIdx.x == 0) ? dbg_all : nullptr;
-    long long tprev = dbg ? clock64() : 0;
-    long long dacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // per-phase cycles (debug only, thread-local)
 
     double* Uc = sm;                                   // [nb][kb][ldu]   columns of G0 -> u_a
     double* Wr = Uc + (size_t)nb * kb * ldu;           // [nb][kb][ldu]   rows of G0    -> w_a
@@ -107,9 +101,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
 
     for (int i0 = 0; i0 < n; i0 += kb) {
         const int kbc = (n - i0 < kb) ? (n - i0) : kb;
-        UPD_TICK(8);                   // flush of the previous block
         __syncthreads();               // previous flush (global G) and sconf visible
-        UPD_TICK(9);
         // ---- stage the kbc columns and rows of G ---------------------------------
         for (int b = 0; b < nb; ++b) {
             const double* Gb = G + (long long)b * p.strideG;
@@ -120,7 +112,6 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
             if (lane < kbc)                                     // rows: a warp copies the kbc contiguous entries of one column
                 for (int c = warp; c < n; c += nwarps) cp_async8(wb + (size_t)lane * ldu + c, Gb + (i0 + lane) + (long long)c * ld);
         }
-        UPD_TICK(0);
         cp_async_wait_all();
         __syncthreads();
         if (tid < nb * kbc) {                                   // G_ii of the block's sites
@@ -128,7 +119,6 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
             sh->gdiag[b][x] = Uc[((size_t)b * kb + x) * ldu + i0 + x];
         }
         __syncthreads();
-        UPD_TICK(1);
 
         int k = 0;                     // accepted flips in this block (delayed factors in slots 0..k-1)
         for (int j = 0; j < kbc; ++j) {
@@ -171,9 +161,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
                     }
                 }
             }
-            if (warp == 0) UPD_TICK(2);
             __syncthreads();
-            UPD_TICK(3);
             const int acc = sh->dec[j & 1];
             if (acc) {
                 // ---- new delayed factors (fields.jl:271-286) ------------------------------
@@ -208,13 +196,9 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
                 // earlier steps (already separated by barriers) and slot j/k entries of its own r.
                 // BUT when k < j another thread's read of ub[k][i] (a < k only) never hits slot k. ok
                 ++k; ++accepted;
-                UPD_TICK(4);
                 __syncthreads();
-                UPD_TICK(5);
             }
         }
-
-        UPD_TICK(6);
         // ---- flush: G_b -= sum_{a<k} u_a w_a^T  (rank-k DMMA update) ---------------------
         if (k > 0) {
             const int g = lane >> 2, t = lane & 3;
@@ -290,9 +274,6 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
             }
         }
     }
-
-    UPD_TICK(7);
-    if (dbg && tid == 0) { for (int i = 0; i < 10; ++i) dbg[i] = dacc[i]; }
     if (tid == 0) {
         if (p.accepted) p.accepted[chain] += accepted;
         if (p.stats && neg_cnt > 0.0) {
@@ -311,33 +292,13 @@ cudaError_t launch_update(const UpdateParams& p, cudaStream_t st)
     if (nt > 256) nt = 256;
     const size_t smem = (size_t)p.nb * 2 * p.kb * ldu * sizeof(double) + sizeof(UpdShared) + (size_t)p.n * 9 + 16;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemAttr attr;
+    cudaError_t e = attr.ensure(update_kernel, smem);
+    if (e != cudaSuccess) return e;
     const double em2a = exp(-2.0 * p.alpha), ep2a = exp(2.0 * p.alpha);
-    static const bool want_dbg = getenv("DQMC_UPD_DBG") != nullptr;
-    static long long* dbg_buf = nullptr;
-    if (want_dbg) {
-        if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
-        cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), st);
-    }
-    update_kernel<<<(unsigned)p.n_chains, nt, smem, st>>>(p, ldu, em2a, ep2a, want_dbg ? dbg_buf : nullptr);
-    ++g_kernel_launches;
-    cudaError_t err = cudaGetLastError();
-    if (want_dbg && err == cudaSuccess) {
-        long long h[16];
-        cudaStreamSynchronize(st);
-        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-        static const char* nm[10] = {"issue staging", "staging wait", "decision(warp0)", "wait decision", "accept update", "sync after accept",
-                                     "pre-flush", "tail", "flush", "sync after flush"};
-        fprintf(stderr, "[upd dbg n=%d kb=%d] cycles of CTA 0 thread 0:", p.n, p.kb);
-        for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%lld", nm[i], h[i]);
-        fprintf(stderr, "\n");
-    }
-    return err;
+    update_kernel<<<(unsigned)p.n_chains, nt, smem, st>>>(p, ldu, em2a, ep2a);
+    count_launch();
+    return cudaGetLastError();
 }
 
 }  // namespace dqmc

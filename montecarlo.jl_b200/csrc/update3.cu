@@ -21,7 +21,6 @@
 #include "common.cuh"
 #include "../../include/dqmc_rng.h"
 #include <math.h>
-#include <stdlib.h>
 #include <algorithm>
 
 namespace dqmc {
@@ -515,17 +514,12 @@ cudaError_t launch_update3(const UpdateParams& p, cudaStream_t st)
     const size_t smem = update3_smem(p.n, p.nb, p.kb);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     const double em2a = exp(-2.0 * p.alpha), ep2a = exp(2.0 * p.alpha);
-    static size_t configured[2] = {0, 0};
-    if (smem > configured[p.nb - 1]) {
-        cudaError_t e = (p.nb == 1)
-            ? cudaFuncSetAttribute(update3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-            : cudaFuncSetAttribute(update3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured[p.nb - 1] = smem;
-    }
+    static SmemAttr attr[2];
+    cudaError_t e = (p.nb == 1) ? attr[0].ensure(update3_kernel<1>, smem) : attr[1].ensure(update3_kernel<2>, smem);
+    if (e != cudaSuccess) return e;
     if (p.nb == 1) update3_kernel<1><<<(unsigned)p.n_chains, 256, smem, st>>>(p, ldu, em2a, ep2a);
     else update3_kernel<2><<<(unsigned)p.n_chains, 256, smem, st>>>(p, ldu, em2a, ep2a);
-    ++g_kernel_launches;
+    count_launch();
     return cudaGetLastError();
 }
 

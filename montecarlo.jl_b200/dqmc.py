@@ -226,21 +226,24 @@ def spin_density_susceptibility(mc, model=None, dir="z"):
 
 # ---- updates (updates/local_updates.jl:70-84, updates/global_updates.jl:229-270, updates/scheduler.jl:236-289)
 class LocalSweep:
+    is_full_sweep = True
+
     def __init__(self, N=1):
         self.N = int(N)
 
 
 class GlobalFlip:
-    pass
+    is_full_sweep = True         # scheduler.jl:67 (default; global_updates.jl does not override it)
 
 
 class GlobalShuffle:
-    pass
+    is_full_sweep = True
 
 
 class SimpleScheduler:
-    """SimpleScheduler(updates...): cycles through the given updates, one per sweep; LocalSweep(N) expands to N
-    local sweeps and at least one local sweep is required (scheduler.jl:267-278)."""
+    """SimpleScheduler(updates...): cycles through the given updates, one per sweep unless an update declares
+    is_full_sweep = False (scheduler.jl:62-67, 281-289).  LocalSweep(N) expands to N local sweeps and at least one
+    local sweep is required (scheduler.jl:267-278)."""
 
     def __init__(self, *updates):
         seq = []
@@ -306,10 +309,8 @@ class DQMC:
         self.ctx.build_stack()
         self._initialized = True
 
-    def sweep_once(self, uniforms=None):
-        """sweep_once! (DQMC.jl:200-225) without the measurement hand-off: one update of the scheduler."""
-        u = self.scheduler.next()
-        self.last_sweep += 1
+    def _apply_update(self, u, uniforms=None):
+        """update(u, mc, model, field) -> acceptance per chain (scheduler.jl:176-181)."""
         if isinstance(u, LocalSweep):
             acc = self.ctx.sweep(1, uniforms)
             self.accepted += acc
@@ -324,6 +325,28 @@ class DQMC:
         self.global_accepted += acc
         self.global_total += 1
         return acc.astype(np.float64)
+
+    def sweep_once(self, uniforms=None):
+        """update(::SimpleScheduler, mc, model) (scheduler.jl:281-289): scheduled updates are executed until one with
+        is_full_sweep(update) == true has run, then last_sweep advances.  is_full_sweep defaults to true for every
+        AbstractUpdate (scheduler.jl:62-67) and neither LocalSweep nor the global updates override it
+        (global_updates.jl:217-270) -- only NoUpdate and ChemicalPotentialTuning return false -- so in the reference a
+        GlobalFlip / GlobalShuffle DOES count as a sweep: SimpleScheduler(LocalSweep(), GlobalFlip()) alternates them,
+        one per sweep.  Returns the acceptance of the last executed update per chain."""
+        while True:
+            u = self.scheduler.next()
+            rate = self._apply_update(u, uniforms)
+            if getattr(u, "is_full_sweep", True):
+                break
+        self.last_sweep += 1
+        return rate
+
+    def max_acceptance(self):
+        """max_acceptance(scheduler) (scheduler.jl:291-299): the largest accepted / total over the update kinds."""
+        rates = [self.accepted.sum() / max(1, self.total * self.ctx.B)]
+        if self.global_total:
+            rates.append(self.global_accepted.sum() / max(1, self.global_total * self.ctx.B))
+        return float(max(rates))
 
     # ---- unequal-time Green's functions (unequal_time_stack.jl, measurements/greens_iterators.jl)
     def greens_kl(self, k, l, chain=None):
@@ -383,18 +406,18 @@ def run(mc: DQMC, *, verbose=False, min_update_rate=0.001):
         mc.init()
     t0 = time.time()
     total = p.thermalization + p.sweeps
-    for i in range(mc.last_sweep + 1, total + 1):
+    min_sweeps = round(1.0 / min_update_rate)                   # DQMC.jl:283
+    while mc.last_sweep < total:
         mc.sweep_once()
-        if i > p.thermalization and (i - p.thermalization) % p.measure_rate == 0 and mc.measurements:
+        i = mc.last_sweep
+        # sweep_once! (DQMC.jl:200-225): measurements fire on last_sweep % measure_rate == 0 after thermalization
+        if i > p.thermalization and i % p.measure_rate == 0 and mc.measurements:
             mc.measure()
+        if i > min_sweeps and mc.max_acceptance() < min_update_rate:          # DQMC.jl:294-307, every sweep
+            mc.sync_field()
+            return "CANCELLED_LOW_ACCEPTANCE"                                   # helpers.jl:17-22
         if verbose and i % p.print_rate == 0:
-            rate = mc.accepted.sum() / max(mc.total * mc.ctx.B, 1)
-            print(f"\t{i}\n\t\tsweep dur: {(time.time() - t0) / i:.3f}s\n\t\tacc rate (local): {rate:.3f}")
-        if i == p.thermalization and p.thermalization > 0:
-            rate = mc.accepted.sum() / max(mc.total * mc.ctx.B, 1)
-            if rate < min_update_rate:
-                mc.sync_field()
-                return "CANCELLED_LOW_ACCEPTANCE"        # DQMC.jl:294-307, helpers.jl:17-22
+            print(f"\t{i}\n\t\tsweep dur: {(time.time() - t0) / i:.3f}s\n\t\tacc rate (local): {mc.max_acceptance():.3f}")
     mc.sync_field()
     return "SUCCESS"
 

@@ -67,3 +67,28 @@ def test_global_update_error_behaviour(b200):
     ctx, _ = make_pair(b200, "square", (2, 2), U=1.0, beta=1.0, B=1, safe_mult=5)
     with pytest.raises(b200.DQMCError):
         ctx.global_update(5)               # stack not built: not at (slice 1, direction +1)
+
+
+def test_consecutive_global_updates_draw_different_uniforms(b200):
+    """SimpleScheduler(LocalSweep(), GlobalFlip(), GlobalShuffle()) performs two global updates without a local sweep in
+    between: their counter-RNG uniforms must differ (site word = running index of the global update), otherwise the
+    second decision is correlated with the first.  Decisions are checked against the ABI's definition of u."""
+    B = 8
+    ctx, chains = make_pair(b200, "square", (2, 2), U=1.0, beta=2.0, B=B, safe_mult=10, mu=0.5, seed=77)
+    ctx.build_stack()
+    M = chains[0].M
+    u0 = np.array([float(philox_uniform(77, b, 0, 2 * M, 0)) for b in range(B)])
+    u1 = np.array([float(philox_uniform(77, b, 0, 2 * M, 1)) for b in range(B)])
+    assert not np.any(u0 == u1)
+    acc0, p0 = ctx.global_update(10)
+    acc1, p1 = ctx.global_update(10)
+    assert np.array_equal(acc0, (p0 > 1.0) | (u0 < p0))
+    assert np.array_equal(acc1, (p1 > 1.0) | (u1 < p1))
+    # a chain whose first flip was rejected sees the same p again; with a shared uniform it could never accept
+    # now -- with independent uniforms it accepts iff u1 < p
+    same = (acc0 == 0)
+    assert np.allclose(p1[same], p0[same], rtol=1e-9)
+    # resume: the running index is restorable like the sweep index
+    ctx.set_global_update_index(0)
+    acc2, p2 = ctx.global_update(10)
+    assert np.array_equal(acc2, (p2 > 1.0) | (u0 < p2))
