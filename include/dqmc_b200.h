@@ -37,6 +37,13 @@ extern "C" {
 
 #define DQMC_FIELD_DENSITY_HIRSCH 0   /* DensityHirschField,  fields.jl:363-395, 1 flavor block  */
 #define DQMC_FIELD_MAGNETIC_HIRSCH 1  /* MagneticHirschField, fields.jl:412-451, 2 flavor blocks */
+#define DQMC_FIELD_DENSITY_GHQ 2      /* DensityGHQField,     fields.jl:565-610, 1 flavor block, conf in 1..4 */
+#define DQMC_FIELD_MAGNETIC_GHQ 3     /* MagneticGHQField,    fields.jl:503-556, 2 flavor blocks, conf in 1..4 */
+/* Gauss-Hermite fields: alpha = sqrt(+-dtau U / 2) must be real (DensityGHQ: U > 0, MagneticGHQ: U < 0; the complex
+ * case is out of scope like every complex matrix type).  A proposal draws x_new = choices[x_old, rand(1:3)] first and
+ * the Metropolis uniform afterwards: both are defined by include/dqmc_rng.h (dqmc_uniform_choice, dqmc_ghq_choice,
+ * dqmc_uniform); explicit uniform tables carry the choice uniforms as a second block per slice visit (see dqmc_sweep).
+ * gamma(x) / eta(x): dqmc_ghq_tables. */
 
 typedef struct dqmc_ctx dqmc_ctx;
 
@@ -85,7 +92,9 @@ int32_t dqmc_set_conf(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, const int8
 int32_t dqmc_get_conf(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, int8_t* conf);
 /* compress(field) = BitArray(conf .== 1) / decompress!(field, bits) (fields.jl:331-334), the wire format of the
  * ConfigRecorder (configurations.jl:92-200): chunks = the UInt64 words of the BitArray (bit i of the column-major
- * N x M array at chunks[i >> 6], position i & 63), ceil(N M / 64) words per chain, packed on the device. */
+ * N x M array at chunks[i >> 6], position i & 63), ceil(N M / 64) words per chain, packed on the device.
+ * GHQ fields (fields.jl:476-489): two bits per value, (v - 1) >> 1 at bit 2 i and (v - 1) & 1 at bit 2 i + 1,
+ * ceil(2 N M / 64) words per chain. */
 int32_t dqmc_get_conf_packed(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, uint64_t* chunks);
 int32_t dqmc_set_conf_packed(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, const uint64_t* chunks);
 
@@ -103,7 +112,9 @@ int32_t dqmc_get_state(const dqmc_ctx* ctx, int32_t* out3);
 /* ---- the sweep ----------------------------------------------------------------------------- */
 /* update(::LocalSweep, mc, model, field) = local_sweep (local_updates.jl:7-14, 82), nsweeps times.
  * uniforms: NULL -> counter RNG (dqmc_rng.h); else host table [nsweeps][n_chains][2M][N] of the
- * Metropolis uniforms.  accepted: [n_chains] accepted flips summed over the nsweeps. */
+ * Metropolis uniforms (Hirsch fields) or [nsweeps][n_chains][2M][2][N] (GHQ fields: per slice visit the N Metropolis
+ * uniforms, then the N choice uniforms u that dqmc_rng.h's dqmc_ghq_choice maps to x_new).
+ * accepted: [n_chains] accepted flips summed over the nsweeps. */
 int32_t dqmc_sweep(dqmc_ctx* ctx, int32_t nsweeps, const double* uniforms, int64_t* accepted);
 /* One sweep with optional teacher forcing and traces, each [n_chains][2M][N]:
  * forced != NULL replays the given accept decisions; probs / decisions (may be NULL) receive
@@ -117,7 +128,9 @@ int32_t dqmc_set_sweep_index(dqmc_ctx* ctx, int64_t sweep);
 
 /* ---- global updates (src/flavors/DQMC/updates/global_updates.jl) ----------------------------------------- */
 /* global_update (:203-219) for every chain: proposed = [n_chains][M][N] configurations (propose_conf! done by the
- * caller: GlobalShuffle, SpatialShuffle, ...) or NULL for GlobalFlip (:237-248, conf -> -conf).  The weight ratio
+ * caller: GlobalShuffle, SpatialShuffle, ...) or NULL for GlobalFlip (:237-248, conf -> -conf; Hirsch fields only).
+ * GHQ fields: like the reference, the ratio carries no gamma(x) factors (propose_global_from_conf has no GHQ method,
+ * :137-179), which is exact for the shuffle updates (they permute the values).  The weight ratio
  * is det(G_old) / det(G_new) from the diagonal factors (inv_det :70-137, propose_global_from_conf :147-179);
  * accepted chains keep the proposal, rejected ones their old configuration; afterwards the stack is rebuilt
  * (accept_global! :181-198) and sits at (slice 1, direction +1).  uniforms: [n_chains] or NULL: counter RNG

@@ -20,6 +20,7 @@
 #ifndef DQMC_RNG_H
 #define DQMC_RNG_H
 
+#include <math.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -54,6 +55,43 @@ DQMC_HD double dqmc_uniform(uint64_t seed, uint64_t chain, uint64_t sweep, uint3
     dqmc_philox4x32_10(c, k0, k1);
     const uint64_t bits = (((uint64_t)c[0] << 32) | (uint64_t)c[1]) >> 11;
     return (double)bits * (1.0 / 9007199254740992.0);
+}
+
+/* Second uniform of the same proposal, from the other two Philox output words: the 4-state Gauss-Hermite fields
+ * (AbstractGHQField, src/flavors/DQMC/fields.jl:464-637) draw the proposed value with `rand(1:3)` before the
+ * Metropolis uniform; the ABI defines that draw as dqmc_ghq_choice(x_old, dqmc_uniform_choice(...)). */
+DQMC_HD double dqmc_uniform_choice(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t step,
+                                   uint32_t site)
+{
+    uint32_t c[4];
+    c[0] = (uint32_t)chain; c[1] = (uint32_t)sweep; c[2] = step; c[3] = site;
+    const uint32_t k0 = (uint32_t)seed ^ (uint32_t)(chain >> 32);
+    const uint32_t k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(sweep >> 32);
+    dqmc_philox4x32_10(c, k0, k1);
+    const uint64_t bits = (((uint64_t)c[2] << 32) | (uint64_t)c[3]) >> 11;
+    return (double)bits * (1.0 / 9007199254740992.0);
+}
+
+/* x_new = choices[x_old, r] with r = 1 + floor(3 u) (fields.jl:528, 540-541, 590): the r-th of {1,2,3,4} \ {x_old}.
+ * A host that owns the integer draw r passes u = (r - 0.5) / 3. */
+DQMC_HD int dqmc_ghq_choice(int x_old, double u)
+{
+    int r = (int)(3.0 * u);
+    if (r > 2) r = 2;
+    if (r < 0) r = 0;
+    const int c = r + 1;
+    return (c >= x_old) ? c + 1 : c;
+}
+
+/* Gauss-Hermite nodes eta(x) and weights gamma(x), x = 1..4, evaluated in double arithmetic exactly like the
+ * reference does (fields.jl:517-519, 579-581: s6 = sqrt(6); gammas = [1 - s6/3, 1 + s6/3, ...];
+ * etas = [-sqrt(6 + 2 s6), -sqrt(6 - 2 s6), ...]); sqrt is correctly rounded on host and device. */
+DQMC_HD void dqmc_ghq_tables(double eta[4], double gamma[4])
+{
+    const double s6 = sqrt(6.0);
+    gamma[0] = 1.0 - s6 / 3.0; gamma[1] = 1.0 + s6 / 3.0; gamma[2] = 1.0 + s6 / 3.0; gamma[3] = 1.0 - s6 / 3.0;
+    eta[0] = -sqrt(6.0 + 2.0 * s6); eta[1] = -sqrt(6.0 - 2.0 * s6);
+    eta[2] = sqrt(6.0 - 2.0 * s6); eta[3] = sqrt(6.0 + 2.0 * s6);
 }
 
 #endif /* DQMC_RNG_H */

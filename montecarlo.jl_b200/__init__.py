@@ -7,7 +7,7 @@ Importing it never touches the CPU oracle; creating a context without a B200 rai
 from . import _lib, build
 from .context import (Context, DQMCError, FIELD_DENSITY_HIRSCH, FIELD_MAGNETIC_HIRSCH, calculate_greens_AVX,
                       rdivp, udt_AVX_pivot, vmul)
-from .dqmc import (DQMC, DQMCParameters, DeviceMeasurement, GlobalFlip, GlobalShuffle, GreensMeasurement, HirschField,
+from .dqmc import (DQMC, DQMCParameters, DeviceMeasurement, Field, GlobalFlip, GlobalShuffle, GreensMeasurement, HirschField,
                    LocalSweep, SimpleScheduler, charge_density_correlation, charge_density_susceptibility,
                    generate_chunks, greens_measurement, interaction_energy, kinetic_energy, occupation, run, run_b,
                    spin_density_correlation, spin_density_susceptibility, sym_exp, total_energy)

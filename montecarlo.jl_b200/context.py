@@ -17,6 +17,8 @@ from . import _lib
 
 FIELD_DENSITY_HIRSCH = 0
 FIELD_MAGNETIC_HIRSCH = 1
+FIELD_DENSITY_GHQ = 2        # 4-state Gauss-Hermite fields (fields.jl:464-637): conf in 1..4
+FIELD_MAGNETIC_GHQ = 3
 
 
 class DQMCError(RuntimeError):
@@ -41,7 +43,9 @@ class Context:
                  device=0, delay_block=0, update_variant=0):
         self._L = _lib.load()
         self.N, self.M, self.kind, self.B = int(n_sites), int(n_slices), int(field_kind), int(n_chains)
-        self.nb = 1 if self.kind == FIELD_DENSITY_HIRSCH else 2
+        self.nb = 2 if (self.kind & 1) else 1
+        self.ghq = self.kind >= FIELD_DENSITY_GHQ
+        self._uf = 2 if self.ghq else 1                  # uniforms per proposal in explicit tables (GHQ: + choice)
         self.ranges = [(int(a), int(b)) for a, b in ranges]
         self.C = len(self.ranges)
         rf = np.array([r[0] for r in self.ranges], dtype=np.int32)
@@ -106,7 +110,7 @@ class Context:
     def get_conf_packed(self, chain0=0, nchains=None):
         """BitArray(conf .== 1).chunks of every chain (fields.jl:331): uint64 (words, nchains)."""
         nchains = self.B - chain0 if nchains is None else nchains
-        words = (self.N * self.M + 63) // 64
+        words = (self.N * self.M * self._uf + 63) // 64          # GHQ: two bits per value
         out = np.zeros((words, nchains), dtype=np.uint64, order="F")
         self._ck(self._L.dqmc_get_conf_packed(self._h, chain0, nchains, out.ctypes.data_as(C.POINTER(C.c_uint64))))
         return out
@@ -116,7 +120,7 @@ class Context:
         chunks = np.asfortranarray(chunks, dtype=np.uint64)
         if chunks.ndim == 1:
             chunks = chunks.reshape(-1, 1, order="F")
-        assert chunks.shape[0] == (self.N * self.M + 63) // 64
+        assert chunks.shape[0] == (self.N * self.M * self._uf + 63) // 64
         self._ck(self._L.dqmc_set_conf_packed(self._h, chain0, chunks.shape[1], chunks.ctypes.data_as(C.POINTER(C.c_uint64))))
 
     # ------------------------------------------------------------------ stack
@@ -137,12 +141,13 @@ class Context:
 
     # ------------------------------------------------------------------ sweeps
     def sweep(self, nsweeps=1, uniforms=None):
-        """-> accepted flips per chain.  uniforms: (nsweeps, B, 2M, N) C-ordered table or None."""
+        """-> accepted flips per chain.  uniforms: (nsweeps, B, 2M, N) C-ordered table (GHQ fields: (nsweeps, B, 2M, 2, N),
+        Metropolis then choice uniforms) or None."""
         acc = np.zeros(self.B, dtype=np.int64)
         u = None
         if uniforms is not None:
             uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
-            assert uniforms.size == nsweeps * self.B * 2 * self.M * self.N
+            assert uniforms.size == nsweeps * self.B * 2 * self.M * self.N * self._uf
             u = _dp(uniforms)
         self._ck(self._L.dqmc_sweep(self._h, int(nsweeps), u, acc.ctypes.data_as(_lib.i64p)))
         return acc
@@ -155,7 +160,7 @@ class Context:
         acc = np.zeros(self.B, dtype=np.int64)
         u = f = None
         if uniforms is not None:
-            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64); assert uniforms.shape == shp
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64); assert uniforms.size == self._uf * probs.size
             u = _dp(uniforms)
         if forced is not None:
             forced = np.ascontiguousarray(forced, dtype=np.uint8); assert forced.shape == shp
@@ -171,7 +176,7 @@ class Context:
         acc = np.zeros(self.B, dtype=np.int64)
         u = f = None
         if uniforms is not None:
-            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64); assert uniforms.shape == shp
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64); assert uniforms.size == self._uf * probs.size
             u = _dp(uniforms)
         if forced is not None:
             forced = np.ascontiguousarray(forced, dtype=np.uint8); assert forced.shape == shp

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "ctx.cuh"
+#include "../../include/dqmc_rng.h"
 
 namespace dqmc { thread_local long long* t_launch_counter = nullptr; }
 
@@ -36,15 +37,23 @@ cudaError_t d2h_mats(dqmc_ctx* c, double* dst, const double* src, long long nmat
 }
 
 // ---- fused diagonal factors ------------------------------------------------------------------
-// interaction_matrix_exp!(..., slice, power) (fields.jl:380-386, 429-438) as a Scale
+// interaction_matrix_exp!(..., slice, power) (fields.jl:380-386, 429-438; GHQ :533-546, 596-602) as a Scale:
+// a look-up table over the 2 (Hirsch) or 4 (GHQ) field values, per flavor block (the magnetic fields flip the sign
+// of the exponent in block 2)
 Scale field_scale(dqmc_ctx* c, int slice, double power)
 {
     Scale s{};
     s.mode = 3;
     s.conf = c->conf + (long long)(slice - 1) * c->N;
     s.cstride = (long long)c->M * c->N;
-    s.ep = exp(power * c->alpha); s.em = exp(-power * c->alpha);
-    s.nb = c->nb; s.flip = (c->kind == DQMC_FIELD_MAGNETIC_HIRSCH) ? 1 : 0;
+    s.nb = c->nb; s.ghq = c->ghq ? 1 : 0;
+    const bool magnetic = (c->kind & 1) != 0;
+    for (int k = 0; k < 4; ++k) {
+        // Hirsch: x = +1 (index 0), -1 (index 1); GHQ: eta(x), x = 1..4
+        const double x = c->ghq ? c->eta[k] : ((k == 0) ? 1.0 : -1.0);
+        s.lut[0][k] = exp(power * c->alpha * x);
+        s.lut[1][k] = magnetic ? exp(-power * c->alpha * x) : s.lut[0][k];
+    }
     return s;
 }
 Scale vec_scale(dqmc_ctx* c, const double* v, bool inverse)
@@ -321,6 +330,7 @@ static cudaError_t sweep_spatial(dqmc_ctx* c, int step, const double* d_unif, lo
     p.conf_slice = c->conf + (long long)(c->current_slice - 1) * c->N; p.cstride = (long long)c->M * c->N;
     p.alpha = c->alpha;
     p.uniforms = d_unif; p.ustride = ustride;
+    if (c->ghq) p.ghq = c->ghq_tab;
     p.seed = c->seed; p.sweep = c->sweep_index; p.step = step; p.chain0 = c->chain_offset;
     p.check_sign = c->check_sign;
     p.accepted = c->accepted; p.stats = c->stats_neg;
@@ -336,9 +346,10 @@ static cudaError_t local_sweep(dqmc_ctx* c, const double* d_unif, const unsigned
                                unsigned char* d_dec)
 {
     const long long ts = (long long)2 * c->M * c->N;
+    const int uf = c->ghq ? 2 : 1;                       // GHQ: Metropolis + choice uniforms per proposal
     for (int step = 0; step < 2 * c->M; ++step) {
         const long long off = (long long)step * c->N;
-        CE(sweep_spatial(c, step, d_unif ? d_unif + off : nullptr, ts, d_forced ? d_forced + off : nullptr,
+        CE(sweep_spatial(c, step, d_unif ? d_unif + uf * off : nullptr, uf * ts, d_forced ? d_forced + off : nullptr,
                          d_probs ? d_probs + off : nullptr, d_dec ? d_dec + off : nullptr, ts));
         CE(propagate(c));
     }
@@ -393,7 +404,7 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     if (!d || !out) { g_create_error = "null argument"; return DQMC_ERR_INVALID; }
     *out = nullptr;
     if (d->n_sites < 1 || d->n_slices < 1 || d->n_chains < 1 || d->n_ranges < 1 ||
-        (d->field_kind != DQMC_FIELD_DENSITY_HIRSCH && d->field_kind != DQMC_FIELD_MAGNETIC_HIRSCH) ||
+        d->field_kind < DQMC_FIELD_DENSITY_HIRSCH || d->field_kind > DQMC_FIELD_MAGNETIC_GHQ ||
         !d->range_first || !d->range_last || !d->hopping_exp_squared || !d->hopping_exp_inv_squared ||
         !d->hopping_exp || !d->hopping_exp_inv) {
         g_create_error = "invalid descriptor"; return DQMC_ERR_INVALID;
@@ -422,7 +433,18 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     }
 
     dqmc_ctx* c = new dqmc_ctx();
-    c->N = d->n_sites; c->M = d->n_slices; c->kind = d->field_kind; c->nb = (c->kind == 0) ? 1 : 2;
+    c->N = d->n_sites; c->M = d->n_slices; c->kind = d->field_kind; c->nb = (c->kind & 1) ? 2 : 1;
+    c->ghq = c->kind >= DQMC_FIELD_DENSITY_GHQ;
+    if (c->ghq) {                                        // fields.jl:513-556, 575-610
+        dqmc_ghq_tables(c->eta, c->ghq_tab.gam);
+        for (int xo = 0; xo < 4; ++xo)
+            for (int xn = 0; xn < 4; ++xn) {
+                const double dE = d->alpha * (c->eta[xn] - c->eta[xo]);
+                c->ghq_tab.er[xo][xn] = exp(dE);
+                c->ghq_tab.ier[xo][xn] = 1.0 / c->ghq_tab.er[xo][xn];
+                c->ghq_tab.ebm[xo][xn] = exp(-dE);
+            }
+    }
     c->B = d->n_chains; c->C = d->n_ranges;
     c->rfirst.assign(d->range_first, d->range_first + c->C);
     c->rlast.assign(d->range_last, d->range_last + c->C);
@@ -496,7 +518,8 @@ int32_t dqmc_set_conf(dqmc_ctx* c, int32_t chain0, int32_t nchains, const int8_t
     if (!conf || !CHAINS_OK(c, chain0, nchains)) FAIL(c, DQMC_ERR_INVALID, "dqmc_set_conf: bad arguments");
     const size_t per = (size_t)c->M * c->N;
     for (size_t i = 0; i < per * nchains; ++i)
-        if (conf[i] != 1 && conf[i] != -1) FAIL(c, DQMC_ERR_INVALID, "dqmc_set_conf: conf values must be +-1");
+        if (c->ghq ? (conf[i] < 1 || conf[i] > 4) : (conf[i] != 1 && conf[i] != -1))
+            FAIL(c, DQMC_ERR_INVALID, c->ghq ? "dqmc_set_conf: conf values must be in 1..4" : "dqmc_set_conf: conf values must be +-1");
     c->generation += 1;
     CK(c, cudaMemcpyAsync(c->conf + per * chain0, conf, per * nchains, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaStreamSynchronize(c->st));
@@ -517,11 +540,11 @@ int32_t dqmc_get_conf(dqmc_ctx* c, int32_t chain0, int32_t nchains, int8_t* conf
 // BitArray(conf .== 1), ceil(N M / 64) UInt64 per chain
 static int32_t conf_packed(dqmc_ctx* c, int32_t chain0, int32_t nchains, uint64_t* chunks, int pack)
 {
-    const long long nbits = (long long)c->M * c->N, wpc = (nbits + 63) / 64;
+    const long long nval = (long long)c->M * c->N, nbits = nval * (c->ghq ? 2 : 1), wpc = (nbits + 63) / 64;
     unsigned long long* d = nullptr;
     CK(c, cudaMallocAsync((void**)&d, (size_t)wpc * nchains * 8, c->st));
     if (!pack) CK(c, cudaMemcpyAsync(d, chunks, (size_t)wpc * nchains * 8, cudaMemcpyHostToDevice, c->st));
-    CK(c, launch_conf_bits(c->conf + nbits * chain0, d, nbits, nchains, pack, c->st));
+    CK(c, launch_conf_bits(c->conf + nval * chain0, d, nval, nchains, pack, c->ghq ? 1 : 0, c->st));
     if (pack) CK(c, cudaMemcpyAsync(chunks, d, (size_t)wpc * nchains * 8, cudaMemcpyDeviceToHost, c->st));
     CK(c, cudaFreeAsync(d, c->st));
     CK(c, cudaStreamSynchronize(c->st));
@@ -602,7 +625,7 @@ int32_t dqmc_sweep(dqmc_ctx* c, int32_t nsweeps, const double* uniforms, int64_t
     ENTER(c);
     if (nsweeps < 0) FAIL(c, DQMC_ERR_INVALID, "dqmc_sweep: nsweeps < 0");
     int32_t rc = require_sweep_start(c, "dqmc_sweep"); if (rc) return rc;
-    const size_t per_sweep = (size_t)c->B * 2 * c->M * c->N;
+    const size_t per_sweep = (size_t)c->B * 2 * c->M * c->N * (c->ghq ? 2 : 1);
     if (uniforms && !c->d_uniforms) CK(c, dalloc(c, &c->d_uniforms, per_sweep));
     CK(c, cudaMemsetAsync(c->accepted, 0, (size_t)c->B * 4, c->st));
     for (int s = 0; s < nsweeps; ++s) {
@@ -618,12 +641,12 @@ int32_t dqmc_sweep_traced(dqmc_ctx* c, const double* uniforms, const uint8_t* fo
 {
     ENTER(c);
     int32_t rc = require_sweep_start(c, "dqmc_sweep_traced"); if (rc) return rc;
-    const size_t per_sweep = (size_t)c->B * 2 * c->M * c->N;
-    if (uniforms && !c->d_uniforms) CK(c, dalloc(c, &c->d_uniforms, per_sweep));
+    const size_t per_sweep = (size_t)c->B * 2 * c->M * c->N, per_unif = per_sweep * (c->ghq ? 2 : 1);
+    if (uniforms && !c->d_uniforms) CK(c, dalloc(c, &c->d_uniforms, per_unif));
     if (forced && !c->d_forced) CK(c, dalloc(c, &c->d_forced, per_sweep));
     if (probs && !c->d_probs) CK(c, dalloc(c, &c->d_probs, per_sweep));
     if (decisions && !c->d_dec) CK(c, dalloc(c, &c->d_dec, per_sweep));
-    if (uniforms) CK(c, cudaMemcpyAsync(c->d_uniforms, uniforms, per_sweep * 8, cudaMemcpyHostToDevice, c->st));
+    if (uniforms) CK(c, cudaMemcpyAsync(c->d_uniforms, uniforms, per_unif * 8, cudaMemcpyHostToDevice, c->st));
     if (forced) CK(c, cudaMemcpyAsync(c->d_forced, forced, per_sweep, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemsetAsync(c->accepted, 0, (size_t)c->B * 4, c->st));
     CK(c, local_sweep(c, uniforms ? c->d_uniforms : nullptr, forced ? c->d_forced : nullptr,
@@ -640,14 +663,15 @@ int32_t dqmc_sweep_spatial(dqmc_ctx* c, const double* uniforms, const uint8_t* f
     if (c->current_slice < 1 || c->current_slice > c->M) FAIL(c, DQMC_ERR_INVALID, "dqmc_sweep_spatial: no current slice");
     const size_t per = (size_t)c->B * 2 * c->M * c->N;   // reuse the per-sweep buffers
     const size_t cnt = (size_t)c->B * c->N;
-    if (uniforms && !c->d_uniforms) CK(c, dalloc(c, &c->d_uniforms, per));
+    const int uf = c->ghq ? 2 : 1;
+    if (uniforms && !c->d_uniforms) CK(c, dalloc(c, &c->d_uniforms, per * uf));
     if (forced && !c->d_forced) CK(c, dalloc(c, &c->d_forced, per));
     if (probs && !c->d_probs) CK(c, dalloc(c, &c->d_probs, per));
     if (decisions && !c->d_dec) CK(c, dalloc(c, &c->d_dec, per));
-    if (uniforms) CK(c, cudaMemcpyAsync(c->d_uniforms, uniforms, cnt * 8, cudaMemcpyHostToDevice, c->st));
+    if (uniforms) CK(c, cudaMemcpyAsync(c->d_uniforms, uniforms, cnt * uf * 8, cudaMemcpyHostToDevice, c->st));
     if (forced) CK(c, cudaMemcpyAsync(c->d_forced, forced, cnt, cudaMemcpyHostToDevice, c->st));
     CK(c, cudaMemsetAsync(c->accepted, 0, (size_t)c->B * 4, c->st));
-    CK(c, sweep_spatial(c, 0, uniforms ? c->d_uniforms : nullptr, c->N, forced ? c->d_forced : nullptr,
+    CK(c, sweep_spatial(c, 0, uniforms ? c->d_uniforms : nullptr, (long long)uf * c->N, forced ? c->d_forced : nullptr,
                         probs ? c->d_probs : nullptr, decisions ? c->d_dec : nullptr, c->N));
     if (probs) CK(c, cudaMemcpyAsync(probs, c->d_probs, cnt * 8, cudaMemcpyDeviceToHost, c->st));
     if (decisions) CK(c, cudaMemcpyAsync(decisions, c->d_dec, cnt, cudaMemcpyDeviceToHost, c->st));

@@ -47,9 +47,10 @@ struct Scale {
     long long stride;
     const int8_t* conf;  // mode 3: conf + chain * cstride + i  (already offset to the slice)
     long long cstride;
-    double ep, em;       // mode 3: value for conf > 0 / conf < 0 in flavor block 0
+    double lut[2][4];    // mode 3: exp(+-power alpha eta(x)) per flavor block; index 0/1 = conf > 0 / < 0 (Hirsch),
+                         //         conf - 1 (GHQ, 4 values)
     int nb;              // flavor blocks per chain (matrix m -> chain m / nb, block m % nb)
-    int flip;            // mode 3: swap ep/em in block 1 (MagneticHirschField)
+    int ghq;             // mode 3: 4-state field (index = conf - 1)
 };
 
 __host__ __device__ inline Scale no_scale() { Scale s{}; s.mode = 0; s.nb = 1; return s; }
@@ -61,9 +62,9 @@ __device__ __forceinline__ double scale_at(const Scale& s, int m, int i)
     if (s.mode == 4) return fmin(1.0, s.vec[(long long)m * s.stride + i]);
     if (s.mode == 5) return 1.0 / fmax(1.0, s.vec[(long long)m * s.stride + i]);
     const int chain = m / s.nb, blk = m - chain * s.nb;
-    const bool up = s.conf[(long long)chain * s.cstride + i] > 0;
-    const bool sw = (s.flip != 0) && (blk == 1);
-    return (up != sw) ? s.ep : s.em;
+    const int x = s.conf[(long long)chain * s.cstride + i];
+    const int code = s.ghq ? ((x - 1) & 3) : ((x > 0) ? 0 : 1);
+    return s.lut[blk][code];
 }
 
 // C[m] = beta * C[m] + alpha * diag(rs) * op(A[m]) * diag(ks) * op(B[m]) * diag(cs) + diag(add_diag)
@@ -111,12 +112,53 @@ struct RdivpParams {
 cudaError_t launch_rdivp(const RdivpParams& p, cudaStream_t st);
 
 // ---- local updates (sweep_spatial) -----------------------------------------
+// Proposal tables of the 4-state Gauss-Hermite fields (fields.jl:525-556, 587-610), indexed [x_old - 1][x_new - 1]:
+// er = exp(alpha (eta_new - eta_old)), ier = 1 / er, ebm = exp(-alpha (eta_new - eta_old)); gam = gamma(x).
+// Filled on the host with libm exp in the reference's own expression order.
+struct GhqTables { double er[4][4], ier[4][4], ebm[4][4], gam[4]; };
+
+// One proposal of sweep_spatial, independent of G: Delta per flavor block, the boson factor exp(-dE_boson) and, for the
+// GHQ fields, gamma(x_new) / gamma(x_old).  Hirsch: fields.jl:388-393, 440-449 (x_new = -x, dE = -2 alpha x);
+// GHQ: fields.jl:525-556, 587-610.  em2a / ep2a = exp(-+2 alpha).
+struct Proposal { double Dl[2]; double bos, gn, go; int xnew; };
+__device__ __forceinline__ Proposal make_proposal(int kind, int x, int xnew_ghq, const GhqTables& T, double em2a, double ep2a)
+{
+    Proposal q;
+    const bool magnetic = (kind & 1) != 0;
+    if (kind < 2) {
+        const double e_dE = (x > 0) ? em2a : ep2a;       // exp(dE), dE = -2 alpha x
+        const double e_mdE = (x > 0) ? ep2a : em2a;
+        q.Dl[0] = e_dE - 1.0;
+        q.Dl[1] = (magnetic ? e_mdE : e_dE) - 1.0;
+        q.bos = magnetic ? 1.0 : e_mdE;
+        q.gn = q.go = 1.0;
+        q.xnew = -x;
+    } else {
+        const int xo = (x - 1) & 3, xn = (xnew_ghq - 1) & 3;
+        q.Dl[0] = T.er[xo][xn] - 1.0;
+        q.Dl[1] = magnetic ? T.ier[xo][xn] - 1.0 : q.Dl[0];
+        q.bos = magnetic ? 1.0 : T.ebm[xo][xn];
+        q.gn = T.gam[xn]; q.go = T.gam[xo];
+        q.xnew = xnew_ghq;
+    }
+    return q;
+}
+// p = exp(-dE_boson) * detratio (local_updates.jl:31); GHQ: detratio * gamma_new / gamma_old first (fields.jl:554, 608)
+__device__ __forceinline__ double proposal_prob(int kind, const Proposal& q, double det)
+{
+    if (kind < 2) return (kind == 0) ? q.bos * det : det;
+    const double d = (det * q.gn) / q.go;
+    return (kind == 2) ? q.bos * d : d;
+}
+
 struct UpdateParams {
     int n, ld, nb, kind, n_chains;
     double* G; long long strideG;            // per matrix
     int8_t* conf_slice; long long cstride;   // conf + slice offset; chain stride
     double alpha;
-    const double* uniforms; long long ustride; // table for this slice visit (per chain stride) or null
+    const double* uniforms; long long ustride; // table for this slice visit (per chain stride) or null; GHQ fields: the
+                                             // N choice uniforms follow the N Metropolis uniforms
+    GhqTables ghq;                           // kind >= 2 only
     unsigned long long seed; long long sweep; int step; long long chain0;
     int check_sign;
     int* accepted;                           // per chain counters (accumulated)
@@ -146,6 +188,7 @@ cudaError_t launch_scale_add(double* O, const double* A, Scale rs, Scale cs, con
                              int n, int ld, long long stride, int batch, cudaStream_t st);
 
 // BitArray(conf .== 1) <-> conf for n_chains configurations of nbits sites x slices each
-cudaError_t launch_conf_bits(int8_t* conf, unsigned long long* chunks, long long nbits, int n_chains, int pack, cudaStream_t st);
+cudaError_t launch_conf_bits(int8_t* conf, unsigned long long* chunks, long long nvalues, int n_chains, int pack, int ghq,
+                             cudaStream_t st);
 
 }  // namespace dqmc

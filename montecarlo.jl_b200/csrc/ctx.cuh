@@ -20,6 +20,7 @@ struct dqmc_ctx {
     int N = 0, M = 0, nb = 1, kind = 0, B = 0, C = 0;
     std::vector<int> rfirst, rlast;
     double alpha = 0.0;
+    bool ghq = false; double eta[4] = {0, 0, 0, 0}; GhqTables ghq_tab{};   // 4-state fields (kind >= 2)
     int check_sign = 1, check_prop = 1;
     unsigned long long seed = 0; long long chain_offset = 0; int device = 0; int kb = 0;
     int ld = 0; long long ms = 0; int nmat = 0; int ldv = 0;

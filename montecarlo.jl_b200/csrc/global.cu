@@ -45,7 +45,7 @@ global_decide_kernel(const double* __restrict__ Dold, const double* __restrict__
         const long long v0 = (long long)chain * nb * N;
         for (int i = 0; i < nb * N; ++i) detratio *= Dnew[v0 + i] / Dold[v0 + i];
         if (nb == 1) detratio = detratio * detratio;
-        const double dE = (kind == 0) ? alpha * (double)tot : 0.0;
+        const double dE = ((kind & 1) == 0) ? alpha * (double)tot : 0.0;   // energy_boson: density fields alpha sum(conf), magnetic 0
         const double p = fabs(exp(-dE) * detratio);
         const double u = uniforms ? uniforms[chain]
                                   : dqmc_uniform(seed, (uint64_t)(chain0 + chain), (uint64_t)sweep, (uint32_t)(2 * M), global_index);
@@ -70,9 +70,12 @@ extern "C" int32_t dqmc_global_update(dqmc_ctx* c, const int8_t* proposed, const
     if (c->current_slice != 1 || c->direction != 1)
         FAIL(c, DQMC_ERR_INVALID, "dqmc_global_update: the stack must be at (slice 1, direction +1) (global_updates.jl:149-150)");
     const size_t per = (size_t)c->M * c->N, tot = per * c->B;
+    if (!proposed && c->ghq)
+        FAIL(c, DQMC_ERR_UNSUPPORTED, "dqmc_global_update: GlobalFlip (conf -> -conf) is not defined for the 4-state GHQ fields");
     if (proposed)
         for (size_t i = 0; i < tot; ++i)
-            if (proposed[i] != 1 && proposed[i] != -1) FAIL(c, DQMC_ERR_INVALID, "dqmc_global_update: conf values must be +-1");
+            if (c->ghq ? (proposed[i] < 1 || proposed[i] > 4) : (proposed[i] != 1 && proposed[i] != -1))
+                FAIL(c, DQMC_ERR_INVALID, "dqmc_global_update: conf values out of range for this field");
     if (!c->conf_backup) CK(c, dalloc(c, &c->conf_backup, tot));
     int* d_acc = nullptr; double* d_p = nullptr; double* d_u = nullptr;
     bool conf_replaced = false;

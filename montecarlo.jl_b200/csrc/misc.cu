@@ -177,31 +177,42 @@ cudaError_t launch_scale_add(double* O, const double* A, Scale rs, Scale cs, con
 // compress(field) = BitArray(conf .== 1) (fields.jl:331): Julia's BitArray keeps bit i of the column-major array
 // in chunks[i >> 6] at bit position i & 63.  One thread per 64-bit chunk; pack != 0: conf -> chunks, else the
 // inverse decompress! (fields.jl:334, conf = 2 bit - 1).
-__global__ void conf_bits_kernel(int8_t* conf, unsigned long long* chunks, long long nbits, long long words_per_chain,
-                                 int n_chains, int pack)
+__global__ void conf_bits_kernel(int8_t* conf, unsigned long long* chunks, long long nvalues, long long words_per_chain,
+                                 int n_chains, int pack, int ghq)
 {
     const long long tot = words_per_chain * n_chains;
+    const int vpw = ghq ? 32 : 64;                       // values per 64-bit word
     for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < tot; w += (long long)gridDim.x * blockDim.x) {
         const long long chain = w / words_per_chain, wi = w - chain * words_per_chain;
-        int8_t* c = conf + chain * nbits + wi * 64;
-        const int nb = (int)((nbits - wi * 64 < 64) ? (nbits - wi * 64) : 64);
+        int8_t* c = conf + chain * nvalues + wi * vpw;
+        const int nv = (int)((nvalues - wi * vpw < vpw) ? (nvalues - wi * vpw) : vpw);
         if (pack) {
             unsigned long long v = 0ull;
-            for (int b = 0; b < nb; ++b) v |= (unsigned long long)(c[b] == 1) << b;
+            if (!ghq) for (int b = 0; b < nv; ++b) v |= (unsigned long long)(c[b] == 1) << b;
+            else                                         // fields.jl:476-480: (1, 2, 3, 4) -> (00, 01, 10, 11), high bit first
+                for (int b = 0; b < nv; ++b) {
+                    const unsigned long long x = (unsigned long long)((c[b] - 1) & 3);
+                    v |= ((x >> 1) << (2 * b)) | ((x & 1ull) << (2 * b + 1));
+                }
             chunks[w] = v;
         } else {
             const unsigned long long v = chunks[w];
-            for (int b = 0; b < nb; ++b) c[b] = (int8_t)(2 * (int)((v >> b) & 1ull) - 1);
+            if (!ghq) for (int b = 0; b < nv; ++b) c[b] = (int8_t)(2 * (int)((v >> b) & 1ull) - 1);
+            else                                         // fields.jl:481-489: 1 + 2 bit1 + bit2
+                for (int b = 0; b < nv; ++b)
+                    c[b] = (int8_t)(1 + 2 * (int)((v >> (2 * b)) & 1ull) + (int)((v >> (2 * b + 1)) & 1ull));
         }
     }
 }
 
-cudaError_t launch_conf_bits(int8_t* conf, unsigned long long* chunks, long long nbits, int n_chains, int pack, cudaStream_t st)
+cudaError_t launch_conf_bits(int8_t* conf, unsigned long long* chunks, long long nvalues, int n_chains, int pack, int ghq,
+                             cudaStream_t st)
 {
     if (n_chains <= 0) return cudaSuccess;
+    const long long nbits = nvalues * (ghq ? 2 : 1);
     const long long wpc = (nbits + 63) / 64, tot = wpc * n_chains;
     long long b = (tot + 255) / 256; if (b > 1184) b = 1184;
-    conf_bits_kernel<<<(unsigned)b, 256, 0, st>>>(conf, chunks, nbits, wpc, n_chains, pack);
+    conf_bits_kernel<<<(unsigned)b, 256, 0, st>>>(conf, chunks, nvalues, wpc, n_chains, pack, ghq);
     count_launch();
     return cudaGetLastError();
 }

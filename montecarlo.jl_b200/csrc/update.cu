@@ -57,7 +57,7 @@ static inline int update_ldu(int n) { return n + (((4 - n) % 16) + 16) % 16; }  
 int update_pick_kb(int n, int nb)
 {
     const long long per_slot = (long long)nb * 2 * update_ldu(n) * 8;
-    long long kb = (200LL * 1024 - 9LL * n) / per_slot;
+    long long kb = (200LL * 1024 - 10LL * n) / per_slot;
     if (kb > 32) kb = 32;
     kb &= ~3LL;
     if (kb < 4) kb = 4;
@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
     UpdShared* sh = (UpdShared*)(Wr + (size_t)nb * kb * ldu);
     double* sunif = (double*)(sh + 1);                 // [n] Metropolis uniforms of this slice visit
     int8_t* sconf = (int8_t*)(sunif + n);              // [n]
+    int8_t* sxnew = sconf + n;                         // [n] proposed value of every site (GHQ: drawn up front)
 
     double* G = p.G + (long long)chain * nb * p.strideG;
     int8_t* conf = p.conf_slice + (long long)chain * p.cstride;
@@ -91,9 +92,15 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
     const unsigned char* forced = p.forced ? p.forced + (long long)chain * p.tstride : nullptr;
 
     for (int i = tid; i < n; i += NT) {
-        sconf[i] = conf[i];
+        const int8_t x = conf[i];
+        sconf[i] = x;
         sunif[i] = utab ? utab[i]
                         : dqmc_uniform(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)p.sweep, (uint32_t)p.step, (uint32_t)i);
+        if (p.kind >= 2) {                             // x_new = choices[x_old, rand(1:3)] (fields.jl:528, 590)
+            const double u2 = utab ? utab[n + i]
+                                   : dqmc_uniform_choice(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)p.sweep, (uint32_t)p.step, (uint32_t)i);
+            sxnew[i] = (int8_t)dqmc_ghq_choice((int)x, u2);
+        } else sxnew[i] = (int8_t)(-x);
     }
 
     int accepted = 0;                  // tracked by every thread identically
@@ -125,20 +132,15 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
             const int i = i0 + j;
             // ---- decision: warp 0 ---------------------------------------------------
             if (warp == 0) {
-                const double x = (double)sconf[i];
-                // dE = -2 alpha x ; exp(dE) = x > 0 ? exp(-2a) : exp(+2a)
-                const double e_dE = (x > 0.0) ? em2a : ep2a;
-                const double e_mdE = (x > 0.0) ? ep2a : em2a;
+                const Proposal pr = make_proposal(p.kind, (int)sconf[i], (int)sxnew[i], p.ghq, em2a, ep2a);
                 double Rv[2], Dl[2];
                 for (int b = 0; b < nb; ++b) {
                     // current G_ii = G0_ii - sum_a u_a[i] w_a[i], kept as a running value per site of the block
                     const double gii = sh->gdiag[b][j];
-                    Dl[b] = ((p.kind == 1 && b == 1) ? e_mdE : e_dE) - 1.0;
+                    Dl[b] = pr.Dl[b];
                     Rv[b] = 1.0 + Dl[b] * (1.0 - gii);
                 }
-                double prob;
-                if (p.kind == 0) prob = e_mdE * ((nb == 1) ? Rv[0] * Rv[0] : Rv[0] * Rv[1]);
-                else prob = Rv[0] * Rv[1];
+                const double prob = proposal_prob(p.kind, pr, (nb == 1) ? Rv[0] * Rv[0] : Rv[0] * Rv[1]);
                 if (lane == 0) {
                     if (p.check_sign && prob < 0.0) {
                         neg_cnt += 1.0; neg_sum += log10(fabs(prob));
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
                         // Delta / R (vldiv22!, fields.jl:176-216) via a Newton reciprocal: the library division is
                         // a ~15-deep dependent FP64 chain on the serial path of every accepted flip
                         for (int b = 0; b < nb; ++b) sh->coef[j & 1][b] = Dl[b] * upd_rcp(Rv[b]);
-                        sconf[i] = (int8_t)(-sconf[i]); conf[i] = sconf[i];
+                        sconf[i] = sxnew[i]; conf[i] = sconf[i];
                     }
                 }
             }
@@ -290,7 +292,7 @@ cudaError_t launch_update(const UpdateParams& p, cudaStream_t st)
     int nt = ((p.n + 31) / 32) * 32;             // one thread per row (flavor blocks in turn)
     if (nt < 64) nt = 64;
     if (nt > 256) nt = 256;
-    const size_t smem = (size_t)p.nb * 2 * p.kb * ldu * sizeof(double) + sizeof(UpdShared) + (size_t)p.n * 9 + 16;
+    const size_t smem = (size_t)p.nb * 2 * p.kb * ldu * sizeof(double) + sizeof(UpdShared) + (size_t)p.n * 10 + 16;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     static SmemAttr attr;
     cudaError_t e = attr.ensure(update_kernel, smem);

@@ -129,6 +129,7 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
     double* sunif = rowv + 2 * nb * kb;                     // [n]
     Upd3Shared* sh = (Upd3Shared*)(sunif + n);
     int8_t* sconf = (int8_t*)(sh + 1);                      // [n]
+    int8_t* sxnew = sconf + n;                              // [n] proposed value of every site (GHQ: drawn up front)
     // work matrices of the serial phase / X build alias the panels (each nb * kb * RP doubles)
     double* Ub = P1;                                        // [nb][kb (site x)][RP (accept a)]; later MU
     double* Wb = P1 + (size_t)nb * kb * RP;                 // [nb][kb (accept a)][RP (site y)]; later MWt
@@ -141,9 +142,15 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
     const unsigned char* forced = p.forced ? p.forced + (long long)chain * p.tstride : nullptr;
 
     for (int i = tid; i < n; i += NT) {
-        sconf[i] = conf[i];
+        const int8_t x = conf[i];
+        sconf[i] = x;
         sunif[i] = utab ? utab[i]
                         : dqmc_uniform(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)p.sweep, (uint32_t)p.step, (uint32_t)i);
+        if (p.kind >= 2) {                                  // x_new = choices[x_old, rand(1:3)] (fields.jl:528, 590)
+            const double u2 = utab ? utab[n + i]
+                                   : dqmc_uniform_choice(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)p.sweep, (uint32_t)p.step, (uint32_t)i);
+            sxnew[i] = (int8_t)dqmc_ghq_choice((int)x, u2);
+        } else sxnew[i] = (int8_t)(-x);
     }
 
     int accepted = 0;
@@ -171,23 +178,19 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
         // the decisions redundantly: (site, Delta / R) of an accepted flip are known to all threads without a
         // broadcast, so an accept costs one CTA barrier (between the extraction of its restricted column / row and
         // their use; colv / rowv are double buffered).
-        double gd[2][2], Dl[2][2], emd[2], un[2];
+        double gd[2][2], un[2];
+        Proposal pr[2];
         int fc[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int j = lane + 32 * h;
             const bool in = j < kbc;
-            const double x = in ? (double)sconf[i0 + j] : 1.0;
-            const double e_dE = (x > 0.0) ? em2a : ep2a;               // exp(dE), dE = -2 alpha x
-            const double e_mdE = (x > 0.0) ? ep2a : em2a;
-            emd[h] = e_mdE;
+            pr[h] = make_proposal(p.kind, in ? (int)sconf[i0 + j] : 1, in ? (int)sxnew[i0 + j] : 1, p.ghq, em2a, ep2a);
             un[h] = in ? sunif[i0 + j] : 2.0;
             fc[h] = (in && forced) ? (int)forced[i0 + j] : -1;
 #pragma unroll
-            for (int b = 0; b < nb; ++b) {
+            for (int b = 0; b < nb; ++b)
                 gd[b][h] = in ? G[(long long)b * p.strideG + (i0 + j) + (long long)(i0 + j) * ld] : 0.0;
-                Dl[b][h] = ((p.kind == 1 && b == 1) ? e_mdE : e_dE) - 1.0;
-            }
         }
         __syncthreads();                                    // panels of the previous block are no longer read
 
@@ -203,12 +206,11 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
                 double Rv[2];
 #pragma unroll
                 for (int b = 0; b < nb; ++b) {
-                    Rv[b] = fma(Dl[b][h], 1.0 - gd[b][h], 1.0);
-                    cf[b][h] = Dl[b][h] * u3_rcp(Rv[b]);               // Delta / R (vldiv22!), speculative
+                    Rv[b] = fma(pr[h].Dl[b], 1.0 - gd[b][h], 1.0);
+                    cf[b][h] = pr[h].Dl[b] * u3_rcp(Rv[b]);            // Delta / R (vldiv22!), speculative
                 }
                 if (nb == 1) cf[1][h] = cf[0][h];
-                if (p.kind == 0) prob[h] = emd[h] * ((nb == 1) ? Rv[0] * Rv[0] : Rv[0] * Rv[1]);
-                else prob[h] = Rv[0] * Rv[1];
+                prob[h] = proposal_prob(p.kind, pr[h], (nb == 1) ? Rv[0] * Rv[0] : Rv[0] * Rv[1]);
                 int a_ = (fc[h] >= 0) ? (fc[h] != 0) : ((prob[h] > 1.0) ? 1 : (un[h] < prob[h]));
                 acc[h] = elig ? a_ : 0;
             }
@@ -236,7 +238,7 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
             const double c1 = __shfl_sync(0xffffffffu, hh ? cf[1][1] : cf[1][0], src);
             const int a = k, j = jacc;
             if (warp == 0 && lane == src) {
-                sconf[i0 + j] = (int8_t)(-sconf[i0 + j]); conf[i0 + j] = sconf[i0 + j];
+                sconf[i0 + j] = sxnew[i0 + j]; conf[i0 + j] = sconf[i0 + j];
                 sh->xs[a] = j; sh->coefs[0][a] = c0; sh->coefs[1][a] = c1;
             }
             double* cvb = colv + (a & 1) * nb * kb;
@@ -485,7 +487,7 @@ static size_t update3_smem(int n, int nb, int kb)
 {
     const int ldu = update3_ldu(n);
     const size_t rs = std::max((size_t)kb * ldu, (size_t)2 * nb * kb * U3_RP);
-    return (2 * rs + (size_t)nb * kb * U3_RP + 4 * nb * kb + n) * sizeof(double) + sizeof(Upd3Shared) + n + 16;
+    return (2 * rs + (size_t)nb * kb * U3_RP + 4 * nb * kb + n) * sizeof(double) + sizeof(Upd3Shared) + 2 * n + 16;
 }
 
 int update3_pick_kb(int n, int nb)

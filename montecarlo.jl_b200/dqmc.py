@@ -15,7 +15,8 @@ import time
 
 import numpy as np
 
-from .context import FIELD_DENSITY_HIRSCH, FIELD_MAGNETIC_HIRSCH, Context
+from .context import (FIELD_DENSITY_GHQ, FIELD_DENSITY_HIRSCH, FIELD_MAGNETIC_GHQ, FIELD_MAGNETIC_HIRSCH,
+                      Context)
 from .models import HubbardModel, choose_field, hopping_matrix
 
 
@@ -68,19 +69,30 @@ def sym_exp(A: np.ndarray) -> np.ndarray:
     return np.asfortranarray((V * np.exp(w)) @ V.T)
 
 
-class HirschField:
-    """DensityHirschField / MagneticHirschField (fields.jl:363-451): alpha and the Int8 conf."""
+class Field:
+    """The Hubbard-Stratonovich fields of the path: DensityHirschField / MagneticHirschField (fields.jl:363-451, conf
+    = +-1) and the 4-node Gauss-Hermite DensityGHQField / MagneticGHQField (fields.jl:464-637, conf in 1..4, real
+    coupling only).  Holds alpha and the Int8 configurations of every chain."""
 
     def __init__(self, name: str, param: DQMCParameters, model: HubbardModel, n_chains: int):
         self.name = name
+        dtU = param.delta_tau * model.U
         if name == "DensityHirschField":
             self.kind = FIELD_DENSITY_HIRSCH
-            self.alpha = math.acosh(math.exp(0.5 * param.delta_tau * model.U))     # fields.jl:372
+            self.alpha = math.acosh(math.exp(0.5 * dtU))                     # fields.jl:372
         elif name == "MagneticHirschField":
             self.kind = FIELD_MAGNETIC_HIRSCH
-            self.alpha = math.acosh(math.exp(-0.5 * param.delta_tau * model.U))    # fields.jl:421
+            self.alpha = math.acosh(math.exp(-0.5 * dtU))                    # fields.jl:421
+        elif name in ("DensityGHQField", "MagneticGHQField"):
+            self.kind = FIELD_DENSITY_GHQ if name == "DensityGHQField" else FIELD_MAGNETIC_GHQ
+            x = (0.5 if self.kind == FIELD_DENSITY_GHQ else -0.5) * dtU      # fields.jl:576 / :514
+            if x < 0:
+                raise NotImplementedError(f"{name} with U = {model.U}: complex coupling sqrt({x}) -- complex matrix types "
+                                          "are outside the B200 sweep path (SURVEY 2)")
+            self.alpha = math.sqrt(x)
         else:
-            raise NotImplementedError(f"{name}: only the real Hirsch fields are on the B200 path (SURVEY 2, row 3)")
+            raise NotImplementedError(f"{name}: not a field of the B200 path")
+        self.ghq = self.kind >= FIELD_DENSITY_GHQ
         self.confs = np.ones((len(model.l), param.slices, n_chains), dtype=np.int8, order="F")
 
     @property
@@ -88,22 +100,37 @@ class HirschField:
         return self.confs[:, :, 0]
 
     def rand(self, rng: np.random.Generator):
-        """rand!(field) (fields.jl:330): iid +-1."""
-        self.confs[...] = rng.choice(np.array([-1, 1], dtype=np.int8), size=self.confs.shape)
+        """rand!(field) (fields.jl:330 iid +-1; :472-473 iid 1..4 for the GHQ fields)."""
+        vals = np.array([1, 2, 3, 4] if self.ghq else [-1, 1], dtype=np.int8)
+        self.confs[...] = rng.choice(vals, size=self.confs.shape)
 
     def compress(self, chain=0):
-        """compress(field) = BitArray(conf .== 1) (fields.jl:331) -> its chunks: uint64 words, bit i of the
-        column-major array at chunks[i >> 6], position i & 63 (Julia's BitArray layout)."""
-        bits = (self.confs[:, :, chain].ravel(order="F") == 1)
+        """compress(field) -> the chunks of the BitArray: uint64 words, bit i at chunks[i >> 6], position i & 63 (Julia's
+        BitArray layout).  Hirsch: BitArray(conf .== 1) (fields.jl:331); GHQ: two bits per value, (v - 1) >> 1 then
+        (v - 1) & 1 (fields.jl:476-480)."""
+        v = self.confs[:, :, chain].ravel(order="F")
+        if self.ghq:
+            bits = np.empty(2 * v.size, dtype=np.uint8)
+            bits[0::2] = (v - 1) >> 1
+            bits[1::2] = (v - 1) & 1
+        else:
+            bits = (v == 1)
         by = np.packbits(bits, bitorder="little")
         by = np.concatenate([by, np.zeros((-len(by)) % 8, dtype=np.uint8)])
         return by.view("<u8").copy()
 
     def decompress(self, chunks, chain=0):
-        """decompress!(field, bits) (fields.jl:334): conf = 2 bit - 1."""
+        """decompress!(field, bits) (fields.jl:334: conf = 2 bit - 1; GHQ :481-489: 1 + 2 bit1 + bit2)."""
         n = self.confs.shape[0] * self.confs.shape[1]
-        bits = np.unpackbits(np.asarray(chunks, dtype="<u8").view(np.uint8), bitorder="little")[:n]
-        self.confs[:, :, chain] = (bits.astype(np.int8) * 2 - 1).reshape(self.confs.shape[:2], order="F")
+        raw = np.unpackbits(np.asarray(chunks, dtype="<u8").view(np.uint8), bitorder="little")
+        if self.ghq:
+            vals = (1 + 2 * raw[0:2 * n:2] + raw[1:2 * n:2]).astype(np.int8)
+        else:
+            vals = raw[:n].astype(np.int8) * 2 - 1
+        self.confs[:, :, chain] = vals.reshape(self.confs.shape[:2], order="F")
+
+
+HirschField = Field        # the name round 1 used
 
 
 class _StackView:
@@ -267,7 +294,7 @@ class DQMC:
         self.model = model
         self.parameters = DQMCParameters(**kwargs)
         self._rng = np.random.default_rng(None if seed == -1 else seed)
-        self.field = HirschField(field or choose_field(model), self.parameters, model, n_chains)
+        self.field = Field(field or choose_field(model), self.parameters, model, n_chains)
         self.field.rand(self._rng)                                  # DQMC.jl:50
         self.measurements = {}
         self.thermalization_measurements = {}

@@ -4,10 +4,18 @@ import numpy as np
 import scipy.linalg as sla
 
 
+def field_values(c, conf):
+    """The number the field couples with: x itself (Hirsch, +-1) or eta(x) (GHQ, x = 1..4; fields.jl:533-546, 596-602)."""
+    if getattr(c, "kind", 0) >= 2:
+        from .model import ghq_tables
+        return ghq_tables()[0][np.asarray(conf, dtype=np.int64) - 1]
+    return np.asarray(conf).astype(float)
+
+
 def slice_B(c, conf, l, b=0):
     """B_l = eT2 * eV_l for flavor block b (stack.jl:319-327, fields.jl:380-386, 429-438)."""
-    s = -1.0 if (c.kind == 1 and b == 1) else 1.0
-    return c.eT2 @ np.diag(np.exp(s * c.alpha * conf[:, l - 1].astype(float)))
+    s = -1.0 if ((c.kind & 1) and b == 1) else 1.0
+    return c.eT2 @ np.diag(np.exp(s * c.alpha * field_values(c, conf[:, l - 1])))
 
 
 def decompose_udt(A):
@@ -69,7 +77,11 @@ def log_weight(c, conf):
         s, ld = np.linalg.slogdet(np.eye(c.N) + P)
         assert s > 0
         lw += ld * (2.0 if c.nb == 1 else 1.0)
-    if c.kind == 0:
-        # exp(alpha x (n_up + n_dn - 1)): the "-1" is the bosonic weight exp(-alpha * sum(conf))
-        lw += -c.alpha * float(conf.astype(np.int64).sum())
+    if (c.kind & 1) == 0:
+        # exp(alpha x (n_up + n_dn - 1)): the "-1" is the bosonic weight exp(-alpha * sum(x)) (GHQ: x -> eta(x))
+        lw += -c.alpha * float(field_values(c, conf).sum())
+    if c.kind >= 2:
+        # exp(dtau U A^2) ~ sum_x gamma(x) exp(alpha eta(x) A) (fields.jl:499-501): the weights gamma(x) of every site / slice
+        from .model import ghq_tables
+        lw += float(np.log(ghq_tables()[1][np.asarray(conf, dtype=np.int64) - 1]).sum())
     return lw

@@ -297,11 +297,12 @@ typedef struct ref_stats {
 } ref_stats;
 
 typedef struct ref_chain {
-    int N, M, nb, kind, C;
+    int N, M, nb, kind, C;               /* kind: 0 DensityHirsch, 1 MagneticHirsch, 2 DensityGHQ, 3 MagneticGHQ */
     int *rfirst, *rlast;                 /* 1-based inclusive ranges (stack.jl:154-158) */
     double alpha;
+    double eta[4], gam[4];               /* GHQ nodes / weights (fields.jl:517-519, 579-581) */
     const double *eT2, *eT2i, *eTh, *eThi; /* exp(-dt T), exp(+dt T), exp(-dt T/2), exp(+dt T/2) */
-    int8_t *conf;                        /* N x M, +-1 (fields.jl:363-368) */
+    int8_t *conf;                        /* N x M, +-1 (fields.jl:363-368) or 1..4 (GHQ, fields.jl:471) */
     double *u_stack, *d_stack, *t_stack; /* (C+1) slots, each nb blocks */
     double *greens, *greens_temp, *Ul, *Ur, *Tl, *Tr, *tmp1, *tmp2, *curr_U;
     double *Dl, *Dr, *eV, *tempv;
@@ -341,6 +342,7 @@ ref_chain *ref_chain_create(int N, int M, int nb, int kind, int C, const int *rf
     c->rfirst = (int *)malloc(sizeof(int) * C); c->rlast = (int *)malloc(sizeof(int) * C);
     memcpy(c->rfirst, rfirst, sizeof(int) * C); memcpy(c->rlast, rlast, sizeof(int) * C);
     c->alpha = alpha; c->eT2 = eT2; c->eT2i = eT2i; c->eTh = eTh; c->eThi = eThi;
+    dqmc_ghq_tables(c->eta, c->gam);
     const size_t nn = (size_t)N * N * nb, nv = (size_t)N * nb;
     c->conf = (int8_t *)malloc((size_t)N * M);
     for (size_t i = 0; i < (size_t)N * M; ++i) c->conf[i] = 1;
@@ -381,6 +383,13 @@ static void interaction_matrix_exp(ref_chain *c, int slice, double power)
 {
     const int N = c->N;
     const int8_t *x = c->conf + (size_t)(slice - 1) * N;
+    if (c->kind >= 2) {
+        /* fields.jl:533-546 (magnetic GHQ: +eta in block 1, -eta in block 2), :596-602 (density GHQ) */
+        for (int i = 0; i < N; ++i) c->eV[i] = exp(power * c->alpha * c->eta[x[i] - 1]);
+        if (c->nb == 2)
+            for (int i = 0; i < N; ++i) c->eV[N + i] = exp(-power * c->alpha * c->eta[x[i] - 1]);
+        return;
+    }
     for (int i = 0; i < N; ++i) c->eV[i] = exp(power * c->alpha * (double)x[i]);
     if (c->nb == 2) {
         const double s = (c->kind == 1) ? -1.0 : 1.0;
@@ -677,11 +686,33 @@ void ref_calculate_greens_at(ref_chain *c, int slice, int safe_mult, double *out
 /* 388-393, 440-449; linalg/updates.jl:7-11, 48-54, 92-97                     */
 /* ------------------------------------------------------------------------ */
 
-/* one proposal at (site i 0-based, current slice); returns p and fills R/Delta */
-static double propose_local(const ref_chain *c, int i, double *Delta, double *R)
+/* one proposal at (site i 0-based, current slice); returns p and fills R/Delta; *x_new = the proposed field value
+ * (the reference's `passthrough`); u_choice: the uniform behind `rand(1:3)` of the GHQ fields */
+static double propose_local(const ref_chain *c, int i, double *Delta, double *R, int8_t *x_new, double u_choice)
 {
     const int n = c->N; const size_t nn = (size_t)n * n;
-    const double x = (double)c->conf[(size_t)(c->current_slice - 1) * n + i];
+    const int8_t xi = c->conf[(size_t)(c->current_slice - 1) * n + i];
+    if (c->kind >= 2) {
+        /* fields.jl:525-556 (magnetic), :587-610 (density) */
+        const int xo = xi, xn = dqmc_ghq_choice(xo, u_choice);
+        *x_new = (int8_t)xn;
+        const double dEb = c->alpha * (c->eta[xn - 1] - c->eta[xo - 1]);
+        const double exp_ratio = exp(dEb);
+        double detratio;
+        if (c->kind == 3) {
+            Delta[0] = exp_ratio - 1.0; Delta[1] = 1.0 / exp_ratio - 1.0;
+            R[0] = 1.0 + Delta[0] * (1.0 - c->greens[IDX(i, i, n)]);
+            R[1] = 1.0 + Delta[1] * (1.0 - c->greens[nn + IDX(i, i, n)]);
+            detratio = R[0] * R[1];
+            return detratio * c->gam[xn - 1] / c->gam[xo - 1];          /* exp(-0.0) * ... */
+        }
+        Delta[0] = exp_ratio - 1.0;
+        R[0] = 1.0 + Delta[0] * (1.0 - c->greens[IDX(i, i, n)]);
+        detratio = R[0] * R[0];
+        return exp(-dEb) * (detratio * c->gam[xn - 1] / c->gam[xo - 1]);  /* local_updates.jl:31 */
+    }
+    const double x = (double)xi;
+    *x_new = (int8_t)(-xi);
     const double dE = -2.0 * c->alpha * x;
     if (c->kind == 0) {
         /* fields.jl:388-393 + :63-66 (nb==1) / :68-75 (nb==2, scalar Delta) */
@@ -702,7 +733,7 @@ static double propose_local(const ref_chain *c, int i, double *Delta, double *R)
 }
 
 /* fields.jl:271-286 + 340-344 */
-static void accept_local(ref_chain *c, int i, const double *Delta, const double *R)
+static void accept_local(ref_chain *c, int i, const double *Delta, const double *R, int8_t x_new)
 {
     const int n = c->N; const size_t nn = (size_t)n * n;
     for (int b = 0; b < c->nb; ++b) {
@@ -717,14 +748,23 @@ static void accept_local(ref_chain *c, int i, const double *Delta, const double 
             for (int k = 0; k < n; ++k) col[k] -= IG[k] * gl;
         }
     }
-    c->conf[(size_t)(c->current_slice - 1) * n + i] *= -1;
+    c->conf[(size_t)(c->current_slice - 1) * n + i] = x_new;     /* fields.jl:342 / :497 */
 }
 
+/* tables: [2M][N] (Hirsch) or [2M][2][N] (GHQ: Metropolis uniforms, then choice uniforms) */
 static double next_uniform(ref_chain *c, int site)
 {
-    if (c->uniforms) return c->uniforms[(size_t)c->step_in_sweep * c->N + site];
+    const size_t uf = (c->kind >= 2) ? 2 : 1;
+    if (c->uniforms) return c->uniforms[(size_t)c->step_in_sweep * c->N * uf + site];
     return dqmc_uniform(c->seed, (uint64_t)c->chain_id, (uint64_t)c->sweep_index,
                         (uint32_t)c->step_in_sweep, (uint32_t)site);
+}
+static double next_choice_uniform(ref_chain *c, int site)
+{
+    if (c->kind < 2) return 0.0;
+    if (c->uniforms) return c->uniforms[(size_t)c->step_in_sweep * c->N * 2 + c->N + site];
+    return dqmc_uniform_choice(c->seed, (uint64_t)c->chain_id, (uint64_t)c->sweep_index,
+                               (uint32_t)c->step_in_sweep, (uint32_t)site);
 }
 
 /* local_updates.jl:23-60.  forced != NULL replays given accept decisions
@@ -735,7 +775,8 @@ int ref_sweep_spatial(ref_chain *c, const uint8_t *forced, double *probs, uint8_
     int accepted = 0;
     double Delta[2], R[2];
     for (int i = 0; i < c->N; ++i) {
-        const double p = propose_local(c, i, Delta, R);
+        int8_t x_new;
+        const double p = propose_local(c, i, Delta, R, &x_new, next_choice_uniform(c, i));
         if (probs) probs[i] = p;
         if (c->check_sign_problem && p < 0.0) {       /* local_updates.jl:40-46 */
             ref_stats *s = &c->stats;
@@ -747,7 +788,7 @@ int ref_sweep_spatial(ref_chain *c, const uint8_t *forced, double *probs, uint8_
         if (forced) acc = forced[i] != 0;
         else acc = (p > 1.0) || (next_uniform(c, i) < p);   /* :53 */
         if (decisions) decisions[i] = (uint8_t)acc;
-        if (acc) { accept_local(c, i, Delta, R); accepted++; }
+        if (acc) { accept_local(c, i, Delta, R, x_new); accepted++; }
     }
     return accepted;
 }
@@ -844,13 +885,15 @@ void ref_multiply_slice_matrix(ref_chain *c, int which, int slice, double *Mx)
 void ref_wrap_greens(ref_chain *c, double *gf, int curr_slice, int direction)
 { wrap_greens(c, gf, curr_slice, direction); }
 /* one proposal + optional accept at (site 0-based) on the current slice */
-double ref_propose_local(ref_chain *c, int site, int accept)
+double ref_propose_local_choice(ref_chain *c, int site, int accept, double u_choice)
 {
     double Delta[2], R[2];
-    const double p = propose_local(c, site, Delta, R);
-    if (accept) accept_local(c, site, Delta, R);
+    int8_t x_new;
+    const double p = propose_local(c, site, Delta, R, &x_new, u_choice);
+    if (accept) accept_local(c, site, Delta, R, x_new);
     return p;
 }
+double ref_propose_local(ref_chain *c, int site, int accept) { return ref_propose_local_choice(c, site, accept, 0.0); }
 
 /* ------------------------------------------------------------------------ */
 /* CPU baseline driver: one chain per thread (the reference is single-        */

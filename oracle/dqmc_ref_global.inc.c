@@ -70,10 +70,10 @@ static void inv_det(ref_chain *c, int slice, int safe_mult)
                                        c->tempv + b * n);
 }
 
-/* fields.jl:395 (density: alpha * sum(conf)) and :451 (magnetic: 0) */
+/* fields.jl:395, 585 (density Hirsch / GHQ: alpha * sum(conf)) and :451, 530 (magnetic: 0) */
 static double energy_boson(const ref_chain *c, const int8_t *conf)
 {
-    if (c->kind != 0) return 0.0;
+    if (c->kind & 1) return 0.0;
     long s = 0;
     for (size_t i = 0; i < (size_t)c->N * c->M; ++i) s += conf[i];
     return c->alpha * (double)s;

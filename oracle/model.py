@@ -109,6 +109,50 @@ def hirsch_alpha(U: float, delta_tau: float, field_kind: int) -> float:
     return math.acosh(math.exp(s * delta_tau * U))
 
 
+# field kinds of the ABI (include/dqmc_b200.h): 0 DensityHirsch, 1 MagneticHirsch, 2 DensityGHQ, 3 MagneticGHQ
+FIELD_KINDS = {"DensityHirschField": 0, "MagneticHirschField": 1, "DensityGHQField": 2, "MagneticGHQField": 3}
+
+
+def ghq_tables():
+    """fields.jl:517-519, 579-581 in the reference's own double arithmetic -> (eta[4], gamma[4], choices[4][3])."""
+    s6 = math.sqrt(6.0)
+    gam = np.array([1 - s6 / 3, 1 + s6 / 3, 1 + s6 / 3, 1 - s6 / 3])
+    eta = np.array([-math.sqrt(6 + 2 * s6), -math.sqrt(6 - 2 * s6), math.sqrt(6 - 2 * s6), math.sqrt(6 + 2 * s6)])
+    choices = np.array([[2, 3, 4], [1, 3, 4], [1, 2, 4], [1, 2, 3]], dtype=np.int8)
+    return eta, gam, choices
+
+
+def ghq_alpha(U: float, delta_tau: float, field_kind: int) -> float:
+    """fields.jl:514 (magnetic GHQ, kind 3): sqrt(-dt U / 2); :576 (density GHQ, kind 2): sqrt(+dt U / 2).  Real only."""
+    x = (0.5 if field_kind == 2 else -0.5) * delta_tau * U
+    if x < 0:
+        raise ValueError("complex GHQ coupling (DensityGHQ needs U > 0, MagneticGHQ U < 0): out of scope")
+    return math.sqrt(x)
+
+
+def field_alpha(U: float, delta_tau: float, field_kind: int) -> float:
+    return hirsch_alpha(U, delta_tau, field_kind) if field_kind < 2 else ghq_alpha(U, delta_tau, field_kind)
+
+
+def ghq_compress(conf) -> np.ndarray:
+    """compress(::AbstractGHQField) (fields.jl:476-480): (1,2,3,4) -> bit pairs (00,01,10,11), high bit first; returns the
+    UInt64 chunks of the BitArray."""
+    v = np.asarray(conf, dtype=np.int64).ravel(order="F") - 1
+    bits = np.empty(2 * v.size, dtype=np.uint8)
+    bits[0::2] = v >> 1
+    bits[1::2] = v & 1
+    by = np.packbits(bits, bitorder="little")
+    by = np.concatenate([by, np.zeros((-len(by)) % 8, dtype=np.uint8)])
+    return by.view("<u8")
+
+
+def ghq_decompress(chunks, shape) -> np.ndarray:
+    """decompress(::AbstractGHQField, c) (fields.jl:481-489): 1 + 2 bit1 + bit2."""
+    n = int(np.prod(shape))
+    bits = np.unpackbits(np.asarray(chunks, dtype="<u8").view(np.uint8), bitorder="little")[:2 * n]
+    return (1 + 2 * bits[0::2] + bits[1::2]).astype(np.int8).reshape(shape, order="F")
+
+
 def choose_field(U: float) -> int:
     """HubbardModel.jl:83: U < 0 -> MagneticHirschField (1) else DensityHirschField (0)."""
     return 1 if U < 0.0 else 0

@@ -92,6 +92,8 @@ def lib():
         L.ref_wrap_greens.argtypes = [C.c_void_p, c_double_p, C.c_int, C.c_int]
         L.ref_propose_local.restype = C.c_double
         L.ref_propose_local.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_propose_local_choice.restype = C.c_double
+        L.ref_propose_local_choice.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.ref_max_threads.restype = C.c_int
         L.ref_run_chains.restype = C.c_double
         L.ref_run_chains.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, c_i64_p]
@@ -179,9 +181,10 @@ class RefChain:
         self.beta = self.M * self.delta_tau
         self.safe_mult = int(safe_mult)
         self.kind = M.choose_field(U) if field_kind is None else int(field_kind)
-        self.nb = 1 if self.kind == 0 else 2
+        self.nb = 2 if (self.kind & 1) else 1
+        self.ghq = self.kind >= 2
         self.U = float(U)
-        self.alpha = M.hirsch_alpha(U, delta_tau, self.kind)
+        self.alpha = M.field_alpha(U, delta_tau, self.kind)
         self.ranges = M.generate_chunks(self.M, self.safe_mult)
         self.C = len(self.ranges)
         self.eT2, self.eT2inv, self.eThalf, self.eThalfinv = M.hopping_exponentials(self.T, delta_tau)
@@ -280,9 +283,10 @@ class RefChain:
         lib().ref_wrap_greens(self._h, _dp(gf), int(curr_slice), int(direction))
         return gf
 
-    def propose_local(self, site, accept=False):
-        """site is 0-based; returns p = exp(-dE_boson) * detratio (local_updates.jl:31)."""
-        return lib().ref_propose_local(self._h, int(site), int(accept))
+    def propose_local(self, site, accept=False, u_choice=0.0):
+        """site is 0-based; returns p = exp(-dE_boson) * detratio (local_updates.jl:31); u_choice: the uniform behind the
+        GHQ fields' rand(1:3) (x_new = dqmc_ghq_choice(x_old, u_choice))."""
+        return lib().ref_propose_local_choice(self._h, int(site), int(accept), float(u_choice))
 
     def sweep_spatial(self, forced=None):
         probs = np.zeros(self.N)

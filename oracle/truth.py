@@ -38,7 +38,12 @@ def lib():
 def slice_diagonals(conf, alpha: float, field_kind: int, block: int) -> np.ndarray:
     """exp(V_l) diagonals [M, N] of flavor block `block` for a Hirsch configuration conf[site, slice]
     (fields.jl:380-386 density: exp(alpha x); :429-438 magnetic: block 2 uses -alpha)."""
-    sign = -1.0 if (field_kind == 1 and block == 1) else 1.0
+    sign = -1.0 if ((field_kind & 1) and block == 1) else 1.0
+    if field_kind >= 2:                                    # GHQ: exp(+-alpha eta(x)), fields.jl:533-546, 596-602
+        from .model import ghq_tables
+        eta = ghq_tables()[0]
+        lut = np.array([math.exp(sign * alpha * e) for e in eta])
+        return np.ascontiguousarray(lut[np.asarray(conf, dtype=np.int64).T - 1], dtype=np.float64)
     ep, em = math.exp(sign * alpha), math.exp(-sign * alpha)
     return np.ascontiguousarray(np.where(np.asarray(conf).T > 0, ep, em), dtype=np.float64)
 

@@ -21,8 +21,9 @@ def rng(seed=0):
     return np.random.default_rng(seed)
 
 
-def rand_confs(g, N, M, B):
-    return np.asfortranarray(g.choice(np.array([-1, 1], dtype=np.int8), size=(N, M, B)))
+def rand_confs(g, N, M, B, ghq=False):
+    vals = np.array([1, 2, 3, 4] if ghq else [-1, 1], dtype=np.int8)
+    return np.asfortranarray(g.choice(vals, size=(N, M, B)))
 
 
 def relerr(a, b):
@@ -30,22 +31,22 @@ def relerr(a, b):
 
 
 def make_pair(b200, kind, Ls, *, U, beta, B=2, safe_mult=10, mu=0.0, seed=11, delta_tau=0.1, delay_block=0,
-              check_prop=True, update_variant=0):
+              check_prop=True, update_variant=0, field_kind=None):
     """-> (Context, [RefChain]) on the same model, conf and RNG key."""
     T = OM.hopping_matrix(kind, Ls, mu=mu)
     N = T.shape[0]
     M = OM.n_slices(beta, delta_tau)
-    fk = OM.choose_field(U)
-    alpha = OM.hirsch_alpha(U, delta_tau, fk)
+    fk = OM.choose_field(U) if field_kind is None else field_kind
+    alpha = OM.field_alpha(U, delta_tau, fk)
     e2, e2i, eh, ehi = OM.hopping_exponentials(T, delta_tau)
-    confs = rand_confs(rng(seed), N, M, B)
+    confs = rand_confs(rng(seed), N, M, B, ghq=fk >= 2)
     ctx = b200.Context(n_sites=N, n_slices=M, field_kind=fk, n_chains=B,
                        ranges=OM.generate_chunks(M, safe_mult), alpha=alpha, hopping_exp_squared=e2,
                        hopping_exp_inv_squared=e2i, hopping_exp=eh, hopping_exp_inv=ehi, seed=seed,
                        delay_block=delay_block, check_propagation_error=check_prop, update_variant=update_variant)
     ctx.set_conf(confs)
     chains = [OR.RefChain(T, U=U, beta=beta, delta_tau=delta_tau, safe_mult=safe_mult, seed=seed, chain_id=b,
-                          conf=confs[:, :, b], check_propagation_error=check_prop) for b in range(B)]
+                          conf=confs[:, :, b], check_propagation_error=check_prop, field_kind=fk) for b in range(B)]
     return ctx, chains
 
 
