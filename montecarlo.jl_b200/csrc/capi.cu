@@ -331,7 +331,7 @@ static cudaError_t sweep_spatial(dqmc_ctx* c, int step, const double* d_unif, lo
     p.alpha = c->alpha;
     p.uniforms = d_unif; p.ustride = ustride;
     if (c->ghq) p.ghq = c->ghq_tab;
-    p.seed = c->seed; p.sweep = c->sweep_index; p.step = step; p.chain0 = c->chain_offset;
+    p.seed = c->seed; p.sweep = c->sweep_index; p.sweep_ptr = c->d_sweep_index; p.step = step; p.chain0 = c->chain_offset;
     p.check_sign = c->check_sign;
     p.accepted = c->accepted; p.stats = c->stats_neg;
     p.forced = d_forced; p.probs = d_probs; p.decisions = d_dec; p.tstride = tstride;
@@ -340,6 +340,8 @@ static cudaError_t sweep_spatial(dqmc_ctx* c, int step, const double* d_unif, lo
     if (c->update_version == 1) return launch_update(p, c->st);
     return launch_update3(p, c->st);
 }
+
+__global__ void bump_kernel(long long* counter) { *counter += 1; }
 
 // local_sweep (local_updates.jl:7-14); tables are device pointers [B][2M][N] or null
 static cudaError_t local_sweep(dqmc_ctx* c, const double* d_unif, const unsigned char* d_forced, double* d_probs,
@@ -354,6 +356,46 @@ static cudaError_t local_sweep(dqmc_ctx* c, const double* d_unif, const unsigned
         CE(propagate(c));
     }
     c->sweep_index += 1;
+    bump_kernel<<<1, 1, 0, c->st>>>(c->d_sweep_index);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// One sweep through a captured CUDA graph.  The first sweeps of a context run eagerly (per-device kernel attributes
+// get configured outside of stream capture), then the launch sequence of local_sweep is captured once per RNG mode
+// and replayed: the update kernels read the sweep index from device memory, everything else in the sequence is the
+// same for every sweep (the stack returns to (slice 1, direction +1) and every buffer to its role).
+static cudaError_t local_sweep_graphed(dqmc_ctx* c, const double* d_unif)
+{
+    const int gi = d_unif ? 1 : 0;
+    if (!c->graph_ok || c->prof_on || c->eager_sweeps < 1) {
+        c->eager_sweeps += 1;
+        return local_sweep(c, d_unif, nullptr, nullptr, nullptr);
+    }
+    if (!c->sweep_graph[gi]) {
+        cudaGraph_t graph = nullptr;
+        const long long l0 = c->launches, s0 = c->sweep_index, g0 = c->generation;
+        cudaError_t e = cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            e = local_sweep(c, d_unif, nullptr, nullptr, nullptr);
+            const cudaError_t e2 = cudaStreamEndCapture(c->st, &graph);
+            if (e == cudaSuccess) e = e2;
+        }
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&c->sweep_graph[gi], graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        c->sweep_graph_launches[gi] = c->launches - l0;
+        c->launches = l0; c->sweep_index = s0; c->generation = g0;      // nothing has executed yet
+        if (e != cudaSuccess) {                              // capture not possible: stay eager for good
+            cudaGetLastError();
+            c->graph_ok = false; c->sweep_graph[gi] = nullptr;
+            c->current_slice = 1; c->current_range = 1; c->direction = 1;
+            return local_sweep(c, d_unif, nullptr, nullptr, nullptr);
+        }
+    }
+    CE(cudaGraphLaunch(c->sweep_graph[gi], c->st));
+    c->launches += c->sweep_graph_launches[gi];
+    c->sweep_index += 1;
+    c->generation += 2 * c->M;
     return cudaSuccess;
 }
 
@@ -391,6 +433,7 @@ int32_t dqmc_destroy(dqmc_ctx* c)
     dqmc_comm_destroy(c);
     ut_destroy(c);
     meas_destroy(c);
+    for (cudaGraphExec_t g : c->sweep_graph) if (g) cudaGraphExecDestroy(g);
     for (void* p : c->allocs) cudaFree(p);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -485,7 +528,7 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
     A_(Dl, vec); A_(Dr, vec); A_(tau, vec); A_(Dgreens, vec);
     A_(udt_scratch, (size_t)c->nmat * udt_reg_scratch_doubles(c->N, c->ld));
     A_(udt_iscratch, (size_t)c->nmat * udt_reg_scratch_ints(c->N));
-    A_(pivot, vec); A_(accepted, (size_t)c->B);
+    A_(pivot, vec); A_(accepted, (size_t)c->B); A_(d_sweep_index, 1);
     A_(stats_neg, (size_t)c->B * 4); A_(stats_prop, (size_t)c->B * 4);
     c->obs_len = 1 + 2 * (long long)c->nb * c->ms;
     A_(obs, (size_t)c->obs_len);
@@ -598,7 +641,15 @@ int32_t dqmc_get_state(const dqmc_ctx* c, int32_t* out3)
     return DQMC_OK;
 }
 
-int32_t dqmc_set_sweep_index(dqmc_ctx* c, int64_t s) { if (!c) return DQMC_ERR_INVALID; c->sweep_index = s; return DQMC_OK; }
+int32_t dqmc_set_sweep_index(dqmc_ctx* c, int64_t s)
+{
+    ENTER(c);
+    c->sweep_index = s;
+    const long long v = s;
+    CK(c, cudaMemcpyAsync(c->d_sweep_index, &v, sizeof(v), cudaMemcpyHostToDevice, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
+    return DQMC_OK;
+}
 
 static int32_t fetch_accepted(dqmc_ctx* c, int64_t* accepted)
 {
@@ -631,7 +682,7 @@ int32_t dqmc_sweep(dqmc_ctx* c, int32_t nsweeps, const double* uniforms, int64_t
     for (int s = 0; s < nsweeps; ++s) {
         if (uniforms)
             CK(c, cudaMemcpyAsync(c->d_uniforms, uniforms + per_sweep * s, per_sweep * 8, cudaMemcpyHostToDevice, c->st));
-        CK(c, local_sweep(c, uniforms ? c->d_uniforms : nullptr, nullptr, nullptr, nullptr));
+        CK(c, local_sweep_graphed(c, uniforms ? c->d_uniforms : nullptr));
     }
     return fetch_accepted(c, accepted);
 }

@@ -160,6 +160,8 @@ struct UpdateParams {
                                              // N choice uniforms follow the N Metropolis uniforms
     GhqTables ghq;                           // kind >= 2 only
     unsigned long long seed; long long sweep; int step; long long chain0;
+    const long long* sweep_ptr;              // device copy of the sweep index (read instead of `sweep` when non-null: a captured
+                                             // CUDA graph of one sweep is replayed with a new index every time)
     int check_sign;
     int* accepted;                           // per chain counters (accumulated)
     double* stats;                           // per chain: [neg_count, neg_sumlog, neg_min, neg_max]

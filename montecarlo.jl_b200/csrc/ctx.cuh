@@ -45,6 +45,11 @@ struct dqmc_ctx {
     // stack state (stack.jl:50-52)
     int current_slice = 0, current_range = 1, direction = 1;
     long long sweep_index = 0;
+    long long* d_sweep_index = nullptr; // device mirror of sweep_index (read by the update kernels; bumped on the stream)
+    // one full local sweep captured as a CUDA graph ([0]: counter RNG, [1]: uniform table): the schedule of a sweep is
+    // data independent, so replaying it removes ~2M x 6 host launches per sweep (the small lattices are launch bound)
+    cudaGraphExec_t sweep_graph[2] = {nullptr, nullptr}; long long sweep_graph_launches[2] = {0, 0};
+    bool graph_ok = true; long long eager_sweeps = 0;
     long long global_index = 0;        // running index of the global updates (site word of their counter-RNG uniform)
     long long launches = 0;            // kernels launched on behalf of this context
     void* nccl_comm = nullptr;         // communicator created by dqmc_comm_init (owned by the context)

@@ -141,14 +141,15 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
     const double* utab = p.uniforms ? p.uniforms + (long long)chain * p.ustride : nullptr;
     const unsigned char* forced = p.forced ? p.forced + (long long)chain * p.tstride : nullptr;
 
+    const unsigned long long sweep_now = (unsigned long long)(p.sweep_ptr ? *p.sweep_ptr : p.sweep);
     for (int i = tid; i < n; i += NT) {
         const int8_t x = conf[i];
         sconf[i] = x;
         sunif[i] = utab ? utab[i]
-                        : dqmc_uniform(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)p.sweep, (uint32_t)p.step, (uint32_t)i);
+                        : dqmc_uniform(p.seed, (uint64_t)(p.chain0 + chain), sweep_now, (uint32_t)p.step, (uint32_t)i);
         if (p.kind >= 2) {                                  // x_new = choices[x_old, rand(1:3)] (fields.jl:528, 590)
             const double u2 = utab ? utab[n + i]
-                                   : dqmc_uniform_choice(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)p.sweep, (uint32_t)p.step, (uint32_t)i);
+                                   : dqmc_uniform_choice(p.seed, (uint64_t)(p.chain0 + chain), sweep_now, (uint32_t)p.step, (uint32_t)i);
             sxnew[i] = (int8_t)dqmc_ghq_choice((int)x, u2);
         } else sxnew[i] = (int8_t)(-x);
     }

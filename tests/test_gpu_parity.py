@@ -505,3 +505,36 @@ def test_conf_packed_on_device(b200):
     ctx.set_conf_packed(packed[:, 1:], chain0=1)
     now = ctx.get_conf()
     assert np.array_equal(now[:, :, 0], -conf[:, :, 0]) and np.array_equal(now[:, :, 1:], conf[:, :, 1:])
+
+
+@pytest.mark.parametrize("kind,Ls,U,fk", [("square", (4, 4), 4.0, None), ("square", (6, 6), -4.0, None),
+                                          ("square", (10, 10), -4.0, None), ("square", (4, 4), -4.0, 3)])
+def test_graph_replayed_sweeps_match_oracle(b200, kind, Ls, U, fk):
+    """dqmc_sweep replays a captured CUDA graph from the second sweep of a context on (the launch schedule of a sweep is
+    data independent; the sweep index is read from device memory).  Five sweeps -- eager, capture, three replays --
+    with the counter RNG and with explicit uniform tables must follow the oracle exactly, and a traced (eager) sweep in
+    between must not disturb the captured one."""
+    for use_table in (False, True):
+        ctx, chains = make_pair(b200, kind, Ls, U=U, beta=1.0, B=2, safe_mult=5, field_kind=fk)
+        ctx.build_stack()
+        for c in chains:
+            c.init()
+        for s in range(5):
+            if s == 3:                                           # an eager traced sweep between replays
+                acc, probs, dec = ctx.sweep_traced()
+                refs = [c.local_sweep(trace=True) for c in chains]
+                for b in range(2):
+                    assert np.array_equal(dec[b], refs[b][2])
+            else:
+                u = None
+                if use_table:
+                    u = np.stack([uniforms_for_sweep(11, b, s, 2 * ctx.M, ctx.N, ghq=ctx.ghq) for b in range(2)])[None]
+                acc = ctx.sweep(1, uniforms=u)
+                refs = [(c.local_sweep(),) for c in chains]
+            G, conf = ctx.greens(), ctx.get_conf()
+            for b, c in enumerate(chains):
+                assert refs[b][0] == acc[b], (s, b)
+                assert np.array_equal(conf[:, :, b], c.get_conf())
+                assert relerr(G[:, :, :, b], c.greens) < GTOL
+        assert ctx.state == (1, 1, 1)
+        assert ctx.kernel_launches() > 0
