@@ -8,10 +8,18 @@
 //
 // sm_100a: tcgen05.mma has no f64 kind, so FP64 tensor math is the warp-level
 // DMMA (PTX mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).  One DMMA is 256 FMA and the
-// SM retires 64 FP64 FMA/clk, so operand delivery is never the limit: tiles are
-// staged with a 3-stage cp.async (LDGSTS) ring into padded shared memory laid out
-// so that every fragment load is bank-conflict free (leading dimension = 4 mod 16
-// doubles).  Roofline: FP64 pipe.
+// SM retires 64 FP64 FMA/clk, so the FP64 pipe is the roofline.
+//
+// Data path: operand tiles are fetched by the TMA engine (cp.async.bulk.tensor.3d, SASS UTMALDG) through
+// tensor maps over (rows, columns, batch), into a multi-stage shared-memory ring whose slots are handed over
+// with transaction mbarriers: one producer warp issues the loads (and evaluates the inner diagonal factor of
+// the k-tile), the consumer warps run DMMA and release the slot -- no CTA barrier in the k loop, no
+// per-thread address arithmetic.  Bank conflicts: the box the TMA engine copies is 4 doubles WIDER than the
+// tile, which makes the leading dimension of the shared tile = 4 (mod 16) doubles -- the conflict-free padded
+// layout -- without any swizzle (the extra columns are never read).  Out-of-bounds parts of a box are
+// zero-filled by the engine, which is all the ragged-edge handling the loads need.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace dqmc {
@@ -22,121 +30,108 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes)
+// ---- mbarrier / TMA primitives ------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned g_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_init(unsigned bar, unsigned count)
 {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(s), "l"(gmem), "r"(src_bytes));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+__device__ __forceinline__ void g_mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "GMW_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra GMD_%=;\n"
+                 "bra GMW_%=;\n"
+                 "GMD_%=:\n"
+                 "}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
 
-// K-major tiles: (x, k) at x * (BK + 4) + k ; BK + 4 = 4 mod 16 for BK = 16 and 32
-
-// Per-thread copy descriptors of one operand tile (XT x BK in "x,k" terms), computed ONCE per CTA:
-// every k-tile then costs one pointer bump and NCH cp.async with precomputed offsets (the div/mod
-// address arithmetic per chunk was ~20 % of the main loop).
-//  KMAJOR == false : global element (x, k) at g[x + k * ld]  (x contiguous) -> smem (x,k) at k*(XT+4) + x
-//  KMAJOR == true  : global element (x, k) at g[k + x * ld]  (k contiguous) -> smem (x,k) at x*(BK+4) + k
-template <int XT, bool KMAJOR, int NTHREADS, int BK>
-struct TileLoader {
-    static constexpr int NCHUNK = XT * BK / 2;                       // 16-byte chunks per tile
-    static constexpr int NCH = (NCHUNK + NTHREADS - 1) / NTHREADS;   // per thread
-    int info[NCH];      // bits 0-4: bytes allowed by the x edge (0 / 8 / 16), bits 8-15: k, bits 16-23: x inside the tile
-    int ld_;
-    const double* g;    // points at (x0, k0) of the current k-tile
-    long long kstep;    // elements to advance per k-tile
-
-    __device__ __forceinline__ void init(const double* base, int ld, int x0, int X, int tid)
-    {
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-            const int c = tid + i * NTHREADS;
-            int x, k, xb;
-            if constexpr (!KMAJOR) {
-                constexpr int CH = XT / 2;
-                k = c / CH; x = (c - k * CH) * 2;
-                xb = (x0 + x + 1 < X) ? 16 : ((x0 + x < X) ? 8 : 0);
-            } else {
-                constexpr int CH = BK / 2;
-                x = c / CH; k = (c - x * CH) * 2;
-                xb = (x0 + x < X) ? 16 : 0;
-            }
-            if (c >= NCHUNK) { xb = 0; x = 0; k = 0; }
-            info[i] = xb | (k << 8) | (x << 16);
-        }
-        ld_ = ld;
-        if constexpr (!KMAJOR) { g = base + x0; kstep = (long long)BK * ld; }
-        else { g = base + (long long)x0 * ld; kstep = BK; }
-    }
-
-    // issue the copies of the k-tile `g` currently points at; krem = K - k0 (> 0)
-    __device__ __forceinline__ void issue(double* s, int krem, int tid)
-    {
-        if (krem >= BK) {
-#pragma unroll
-            for (int i = 0; i < NCH; ++i) {
-                if (NCHUNK % NTHREADS != 0 && tid + i * NTHREADS >= NCHUNK) continue;
-                const int xb = info[i] & 31, k = (info[i] >> 8) & 255, x = info[i] >> 16;
-                const int so = KMAJOR ? (k + x * ld_) : (x + k * ld_);
-                const int dof = KMAJOR ? (x * (BK + 4) + k) : (k * (XT + 4) + x);
-                cp_async16(s + dof, xb ? (g + so) : g, xb);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < NCH; ++i) {
-                if (NCHUNK % NTHREADS != 0 && tid + i * NTHREADS >= NCHUNK) continue;
-                const int xb = info[i] & 31, k = (info[i] >> 8) & 255, x = info[i] >> 16;
-                const int so = KMAJOR ? (k + x * ld_) : (x + k * ld_);
-                const int dof = KMAJOR ? (x * (BK + 4) + k) : (k * (XT + 4) + x);
-                int bytes;
-                if constexpr (!KMAJOR) bytes = (k < krem) ? xb : 0;
-                else bytes = xb ? ((k + 1 < krem) ? 16 : ((k < krem) ? 8 : 0)) : 0;
-                cp_async16(s + dof, bytes ? (g + so) : g, bytes);
-            }
-        }
-    }
-    __device__ __forceinline__ void advance() { g += kstep; }
-};
-
+// Shared tiles, in "x, k" terms (x = m for A, n for B):
+//  KMAJOR == false : global element (x, k) at g[x + k * ld]  (x contiguous) -> smem (x, k) at k * (XT + 4) + x
+//  KMAJOR == true  : global element (x, k) at g[k + x * ld]  (k contiguous) -> smem (x, k) at x * (BK + 4) + k
+// both leading dimensions are = 4 (mod 16) doubles for XT in {32, 48, 64} and BK = 16: conflict-free fragment loads
 template <int XT, bool KMAJOR, int BK>
 __device__ __forceinline__ double tile_at(const double* s, int x, int k)
 {
     if constexpr (!KMAJOR) return s[k * (XT + 4) + x];
     else return s[x * (BK + 4) + k];
 }
-
 template <int XT, bool KMAJOR, int BK> __host__ __device__ constexpr int tile_elems() { return KMAJOR ? XT * (BK + 4) : BK * (XT + 4); }
 
 template <int BM, int BN, int WM, int WN, bool TA, bool TB, int BK, int STAGES, int MINB>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
-gemm_kernel(const GemmParams p)
+__global__ void __launch_bounds__(((BM / WM) * (BN / WN) + 1) * 32, MINB)
+gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p)
 {
-    constexpr int NWM = BM / WM, NWN = BN / WN, NT = NWM * NWN * 32;
+    constexpr int NWM = BM / WM, NWN = BN / WN, NCW = NWM * NWN;      // consumer warps; warp NCW is the producer
     constexpr int MI = WM / 8, NJ = WN / 8;
     // A tile is K-major in global iff transA (A stored K x M, k contiguous)
     constexpr bool AK = TA;
     // B tile (n, k): global B is K x N col-major (k contiguous) unless transB
     constexpr bool BKM = !TB;
     constexpr int AE = tile_elems<BM, AK, BK>(), BE = tile_elems<BN, BKM, BK>();
+    static_assert((AE * 8) % 128 == 0 && (BE * 8) % 128 == 0, "TMA destinations stay 128-byte aligned");
 
-    extern __shared__ __align__(16) double smem[];
-    double* As = smem;
-    double* Bs = smem + STAGES * AE;
-    double* Ks = Bs + STAGES * BE;          // [STAGES][BK] inner scale
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    double* As = smem;                                   // [STAGES][AE]
+    double* Bs = smem + STAGES * AE;                     // [STAGES][BE]
+    double* Ks = Bs + STAGES * BE;                       // [STAGES][BK] inner scale of the k-tile
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(Ks + STAGES * BK);   // full[STAGES], empty[STAGES]
+    const unsigned full0 = g_smem_u32(bars), empty0 = g_smem_u32(bars + STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, mat = blockIdx.z;
+    const int KT = (p.K + BK - 1) / BK;
+    const bool has_ks = p.ks.mode != 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { g_mbar_init(full0 + 8 * s, 1); g_mbar_init(empty0 + 8 * s, NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ================================ producer warp ================================
+        const int za = p.strideA ? mat : 0, zb = p.strideB ? mat : 0;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int st = kt % STAGES, k0 = kt * BK;
+            if (kt >= STAGES) g_mbar_wait(empty0 + 8 * st, (unsigned)((kt / STAGES) - 1) & 1u);
+            if (has_ks && lane < BK) {
+                const int gk = k0 + lane;
+                Ks[st * BK + lane] = (gk < p.K) ? scale_at(p.ks, mat, gk) : 0.0;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                g_mbar_arrive_expect_tx(full0 + 8 * st, (unsigned)((AE + BE) * sizeof(double)));
+                if constexpr (!AK) tma_load_3d(g_smem_u32(As + st * AE), &mapA, m0, k0, za, full0 + 8 * st);
+                else tma_load_3d(g_smem_u32(As + st * AE), &mapA, k0, m0, za, full0 + 8 * st);
+                if constexpr (!BKM) tma_load_3d(g_smem_u32(Bs + st * BE), &mapB, n0, k0, zb, full0 + 8 * st);
+                else tma_load_3d(g_smem_u32(Bs + st * BE), &mapB, k0, n0, zb, full0 + 8 * st);
+            }
+        }
+        return;
+    }
+
+    // ================================ consumer warps ================================
     const int g = lane >> 2, t = lane & 3;
     const int wm0 = (warp % NWM) * WM, wn0 = (warp / NWM) * WN;
-    const bool has_ks = p.ks.mode != 0;
     const bool has_rs = p.rs.mode != 0, has_cs = p.cs.mode != 0;
-
-    // one CTA per output tile (a persistent variant with a cross-tile cp.async ring was measured
-    // slower: 25.8 vs 26.8 TFLOP/s at K = 256 -- the block scheduler already staggers the 8 waves)
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, mat = blockIdx.z;
-    const double* A = p.A + (long long)mat * p.strideA;
-    const double* B = p.B + (long long)mat * p.strideB;
     double* C = p.C + (long long)mat * p.strideC;
-    const int KT = (p.K + BK - 1) / BK;
 
     // C read-modify-write without scalings (the panel updates of rdivp.cu):
     // the accumulators start from beta / alpha * C, so the loads of C overlap the main loop instead of sitting
@@ -162,41 +157,12 @@ gemm_kernel(const GemmParams p)
         }
     }
 
-    TileLoader<BM, AK, NT, BK> la;
-    TileLoader<BN, BKM, NT, BK> lb;
-    la.init(A, p.lda, m0, p.M, tid);
-    lb.init(B, p.ldb, n0, p.N, tid);
-    int kr_i = 0;                            // k-tile the loaders point at
-    auto issue = [&](int stage) {
-        const int k0 = kr_i * BK;
-        la.issue(As + stage * AE, p.K - k0, tid);
-        lb.issue(Bs + stage * BE, p.K - k0, tid);
-        la.advance(); lb.advance();
-        if (has_ks && tid < BK) {
-            const int gk = k0 + tid;
-            Ks[stage * BK + tid] = (gk < p.K) ? scale_at(p.ks, mat, gk) : 0.0;
-        }
-        ++kr_i;
-    };
-
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT) issue(s);
-        cp_async_commit();
-    }
-
-    int stage = 0, stage_n = STAGES - 1;     // stage being computed / stage the next issue goes to
     for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        if (kt + STAGES - 1 < KT) issue(stage_n);
-        cp_async_commit();
-        if (++stage_n == STAGES) stage_n = 0;
-
-        const double* as = As + stage * AE;
-        const double* bs = Bs + stage * BE;
-        const double* ks = Ks + stage * BK;
-        if (++stage == STAGES) stage = 0;
+        const int st = kt % STAGES;
+        g_mbar_wait(full0 + 8 * st, (unsigned)(kt / STAGES) & 1u);
+        const double* as = As + st * AE;
+        const double* bs = Bs + st * BE;
+        const double* ks = Ks + st * BK;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
             const int k = kk * 4 + t;
@@ -215,8 +181,9 @@ gemm_kernel(const GemmParams p)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
+        __syncwarp();
+        if (lane == 0) g_mbar_arrive(empty0 + 8 * st);   // this warp is done with the slot
     }
-    cp_async_wait<0>();
 
     // epilogue: thread owns C[row = g, cols = 2t, 2t+1] of every 8x8 block
 #pragma unroll
@@ -241,18 +208,59 @@ gemm_kernel(const GemmParams p)
     }
 }
 
+// ---- host: tensor maps ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// (dim0 = contiguous rows of the stored matrix, dim1 = its columns, dim2 = batch); box0 x box1 x 1 doubles per load
+static cudaError_t make_map(CUtensorMap* map, const double* base, int rows, int cols, int ld, long long stride, int batch,
+                            int box0, int box1)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return cudaErrorNotSupported;
+    const bool shared = stride == 0;
+    cuuint64_t dims[3] = {(cuuint64_t)rows, (cuuint64_t)cols, (cuuint64_t)(shared ? 1 : batch)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8ull, (cuuint64_t)(shared ? (long long)ld * cols : stride) * 8ull};
+    cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int BM, int BN, int WM, int WN, bool TA, bool TB, int BK = 16, int STAGES = 3, int MINB = 4>
 static cudaError_t launch_cfg(const GemmParams& p, cudaStream_t st)
 {
-    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    constexpr int NT = ((BM / WM) * (BN / WN) + 1) * 32;
     constexpr int AE = tile_elems<BM, TA, BK>(), BE = tile_elems<BN, !TB, BK>();
-    constexpr int smem = (STAGES * (AE + BE) + STAGES * BK) * (int)sizeof(double);
+    constexpr int smem = (STAGES * (AE + BE) + STAGES * BK) * (int)sizeof(double) + 2 * STAGES * 8 + 128;
     auto kern = gemm_kernel<BM, BN, WM, WN, TA, TB, BK, STAGES, MINB>;
     static SmemAttr attr;
     cudaError_t e = attr.ensure(kern, smem);
     if (e != cudaSuccess) return e;
+    CUtensorMap mapA, mapB;
+    // A: M x K (or K x M when transposed), B: K x N (or N x K when transposed), as stored
+    if (!TA) e = make_map(&mapA, p.A, p.M, p.K, p.lda, p.strideA, p.batch, BM + 4, BK);
+    else e = make_map(&mapA, p.A, p.K, p.M, p.lda, p.strideA, p.batch, BK + 4, BM);
+    if (e != cudaSuccess) return e;
+    if (TB) e = make_map(&mapB, p.B, p.N, p.K, p.ldb, p.strideB, p.batch, BN + 4, BK);
+    else e = make_map(&mapB, p.B, p.K, p.N, p.ldb, p.strideB, p.batch, BK + 4, BN);
+    if (e != cudaSuccess) return e;
     dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, p.batch);
-    kern<<<grid, NT, smem, st>>>(p);
+    kern<<<grid, NT, smem, st>>>(mapA, mapB, p);
     count_launch();
     return cudaGetLastError();
 }
@@ -266,11 +274,9 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
         return mm * nn / ((double)p.M * (double)p.N);
     };
     const double w64 = waste(64, 64), w48 = waste(48, 48), w32 = waste(32, 32);
-    // Measured on 296 x 256^3 (profiles/r1_summary.md): 64 x 64 tiles, 2 stages, 5 CTAs/SM is the best of 22 variants
-    // (128 x 64 / 128 x 128 tiles, BK = 8 / 32, 3-4 stages were all slower: more co-resident CTAs at independent phases
-    // beat larger tiles); n = 288: a 96 x 96 CTA tile covers it exactly like 48 x 48 does but measured slower.
-    if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9)
-        return launch_cfg<64, 64, 32, 32, TA, TB, 16, 2, 5>(p, st);
+    // Measured on 296 x 256^3: BK = 16 with 4 stages at 3 CTAs/SM 28.98 TFLOP/s, 3 stages 28.44, BK = 32 with 2 stages 28.99,
+    // 2 CTAs/SM 25.2; the cp.async ring this replaces reached 28.4 with 5 CTAs/SM (DMMA pipe 81 % busy either way)
+    if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4, 3>(p, st);
     if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
     return launch_cfg<32, 32, 16, 16, TA, TB>(p, st);
 }
@@ -278,7 +284,9 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
 cudaError_t launch_gemm(const GemmParams& p, cudaStream_t st)
 {
     if (p.batch <= 0 || p.M <= 0 || p.N <= 0) return cudaSuccess;
-    if ((p.lda & 1) || (p.ldb & 1)) return cudaErrorInvalidValue;   // 16-byte cp.async columns
+    // TMA: 16-byte aligned base addresses and strides (even leading dimensions, even offsets)
+    if ((p.lda & 1) || (p.ldb & 1) || (p.strideA & 1) || (p.strideB & 1) ||
+        ((uintptr_t)p.A & 15) || ((uintptr_t)p.B & 15)) return cudaErrorInvalidValue;
     if (!p.transA && !p.transB) return launch_tiles<false, false>(p, st);
     if (!p.transA && p.transB) return launch_tiles<false, true>(p, st);
     if (p.transA && !p.transB) return launch_tiles<true, false>(p, st);
