@@ -230,6 +230,15 @@ int32_t dqmc_get_measurements(dqmc_ctx* ctx, int32_t chain0, int32_t nchains, do
  * calls; dqmc_reduce_observables all-reduces it together with the Green's function block. */
 int32_t dqmc_measurement_buffer(dqmc_ctx* ctx, void** device_ptr, int64_t* n_doubles);
 int32_t dqmc_get_measurement_stats(dqmc_ctx* ctx, double* counts /* [2] */, double* sum, double* sumsq);
+/* Log-binning of every observable element (the LogBinner of BinningAnalysis.jl 0.6 that backs a DQMCMeasurement,
+ * measurements/generic.jl:62-65, 92-95, 586-587): level 0 accumulates every measured value, level l + 1 the mean of two
+ * successive values of level l, per chain; {count, sum, sum of squares} of each level are summed over the chains of the
+ * context (and over ranks by dqmc_reduce_observables).  L = dqmc_binning_levels().  counts: [2][L] (equal time, time
+ * integral), sum / sumsq: [L][length].  std_error(level l) = sqrt((sumsq/count - (sum/count)^2) / (count - 1)); its growth
+ * with l is the autocorrelation-aware error estimate.  (Third-party arithmetic: parity unpinned, see DESIGN.md.) */
+int32_t dqmc_binning_levels(void);
+int32_t dqmc_get_measurement_binning(dqmc_ctx* ctx, double* counts, double* sum, double* sumsq);
+int32_t dqmc_measurement_binning_buffer(dqmc_ctx* ctx, void** device_ptr, int64_t* n_doubles);
 
 /* ---- operator level: the reference's linalg "operator API", batched over host arrays ------- */
 /* vmul!(C, op(A), op(B)) (linalg/real.jl:7-15, 72-102) */

@@ -96,6 +96,9 @@ def load():
         "dqmc_get_measurements": (i32, [vp, i32, i32, dp]),
         "dqmc_measurement_buffer": (i32, [vp, C.POINTER(vp), i64p]),
         "dqmc_get_measurement_stats": (i32, [vp, dp, dp, dp]),
+        "dqmc_binning_levels": (i32, []),
+        "dqmc_get_measurement_binning": (i32, [vp, dp, dp, dp]),
+        "dqmc_measurement_binning_buffer": (i32, [vp, C.POINTER(vp), i64p]),
         "dqmc_accumulate_greens": (i32, [vp]),
         "dqmc_observable_buffer": (i32, [vp, C.POINTER(vp), i64p]),
         "dqmc_reduce_observables": (i32, [vp, vp]),

@@ -355,6 +355,24 @@ class Context:
         self._ck(self._L.dqmc_get_measurement_stats(self._h, _dp(cnt), _dp(s), _dp(s2)))
         return cnt[0], cnt[1], self._split_obs(s), self._split_obs(s2)
 
+    def measurement_binning(self):
+        """Log-binning levels of every observable element (LogBinner semantics): -> (counts[2, L], sums, sumsqs) with
+        sums / sumsqs dicts of arrays whose leading axis is the level."""
+        L, n = int(self._L.dqmc_binning_levels()), self._obs_off[-1]
+        cnt = np.zeros((2, L)); s = np.zeros((L, n)); s2 = np.zeros((L, n))
+        self._ck(self._L.dqmc_get_measurement_binning(self._h, _dp(cnt), _dp(s), _dp(s2)))
+        return cnt, self._split_obs(s), self._split_obs(s2)
+
+    def binning_std_errors(self, key, time_integral=False):
+        """std_error of observable `key` at every populated binning level (per element) -> (levels, n_l, err[levels, ...])."""
+        cnt, s, s2 = self.measurement_binning()
+        c = cnt[1 if time_integral else 0]
+        lv = np.nonzero(c > 1)[0]
+        shape = (-1,) + (1,) * (s[key].ndim - 1)
+        mean = s[key][lv] / c[lv].reshape(shape)
+        var = np.maximum(s2[key][lv] / c[lv].reshape(shape) - mean ** 2, 0.0)
+        return lv, c[lv], np.sqrt(var / (c[lv].reshape(shape) - 1))
+
     # ------------------------------------------------------------------ observables
     def accumulate_greens(self):
         self._ck(self._L.dqmc_accumulate_greens(self._h))

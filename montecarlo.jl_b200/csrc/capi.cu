@@ -951,6 +951,9 @@ int32_t dqmc_reduce_observables(dqmc_ctx* c, void* comm)
         void* mptr = nullptr; int64_t mlen = 0;
         if (c->meas && dqmc_measurement_buffer(c, &mptr, &mlen) == DQMC_OK && mlen > 0)
             if (n.AllReduce(mptr, mptr, (size_t)mlen, 8, 0, comm, c->st) != 0) FAIL(c, DQMC_ERR_CUDA, "ncclAllReduce failed");
+        // ... and their log-binning levels ({count, sum, sum of squares} per level)
+        if (c->meas && dqmc_measurement_binning_buffer(c, &mptr, &mlen) == DQMC_OK && mlen > 0)
+            if (n.AllReduce(mptr, mptr, (size_t)mlen, 8, 0, comm, c->st) != 0) FAIL(c, DQMC_ERR_CUDA, "ncclAllReduce failed");
     }
     CK(c, cudaStreamSynchronize(c->st));
     return DQMC_OK;

@@ -32,7 +32,14 @@ struct dqmc_meas {
     double* res = nullptr;         // [chain][len]: values of the last measurement of every chain
     double* acc = nullptr;         // [count_equal_time, count_time_integral | sum[len] | sumsq[len]]
     double* h_res = nullptr;
+    // log-binning (LogBinner of BinningAnalysis.jl, the accumulator behind every DQMCMeasurement,
+    // measurements/generic.jl:62-65, 586-587): level 0 takes every value, level l + 1 the mean of two successive values
+    // of level l.  Every chain is its own time series; the level statistics are summed over the chains.
+    double* lb_pend = nullptr;     // [chain][level][len] value waiting for its partner (the compressors)
+    double* lb_acc = nullptr;      // [counts: 2 x LB_LEVELS | sum[LB_LEVELS][len] | sumsq[LB_LEVELS][len]]
+    long long pushes[2] = {0, 0};  // measurements committed so far: equal time, time integral
 };
+constexpr int LB_LEVELS = 20;      // 2^19 measurements per chain before the top level stops pairing
 
 void meas_destroy(dqmc_ctx* c) { delete c->meas; c->meas = nullptr; }
 
@@ -132,15 +139,36 @@ __global__ void meas_zero_kernel(double* res, long long res_stride, int o0, int 
 }
 
 // push!(observable, temp) for every chain: {count, sum, sum of squares}
+// nl = number of levels this push reaches = 1 + trailing ones of the number of earlier pushes (capped at LB_LEVELS)
 __global__ void meas_commit_kernel(const double* res, long long res_stride, int o0, int o1, int n_chains,
-                                   double* acc, int which_count, int len)
+                                   double* acc, int which_count, int len, double* lb_pend, double* lb_acc, int nl)
 {
     for (int e = o0 + blockIdx.x * blockDim.x + threadIdx.x; e < o1; e += gridDim.x * blockDim.x) {
         double s = 0.0, s2 = 0.0;
-        for (int b = 0; b < n_chains; ++b) { const double x = res[(long long)b * res_stride + e]; s += x; s2 += x * x; }
+        double ls[LB_LEVELS], ls2[LB_LEVELS];
+        for (int l = 0; l < nl; ++l) ls[l] = ls2[l] = 0.0;
+        for (int b = 0; b < n_chains; ++b) {
+            const double x = res[(long long)b * res_stride + e];
+            s += x; s2 += x * x;
+            // LogBinner push!: accumulate at the level, then pair with the waiting value and move up
+            double v = x;
+            double* pend = lb_pend + ((long long)b * LB_LEVELS) * len + e;
+            for (int l = 0; l < nl; ++l) {
+                ls[l] += v; ls2[l] += v * v;
+                if (l + 1 < nl) v = 0.5 * (pend[(long long)l * len] + v);
+                else pend[(long long)l * len] = v;
+            }
+        }
         acc[2 + e] += s; acc[2 + len + e] += s2;
+        for (int l = 0; l < nl; ++l) {
+            lb_acc[2 * LB_LEVELS + (long long)l * len + e] += ls[l];
+            lb_acc[2 * LB_LEVELS + ((long long)LB_LEVELS + l) * len + e] += ls2[l];
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) acc[which_count] += (double)n_chains;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        acc[which_count] += (double)n_chains;
+        for (int l = 0; l < nl; ++l) lb_acc[which_count * LB_LEVELS + l] += (double)n_chains;
+    }
 }
 
 static cudaError_t launch_pair(dqmc_ctx* c, const double* G00, const double* G0l, const double* Gl0,
@@ -167,8 +195,11 @@ static cudaError_t launch_commit(dqmc_ctx* c, int o0, int o1, int which_count)
 {
     dqmc_meas* m = c->meas;
     const int blocks = std::min(148, (o1 - o0 + 255) / 256);
+    int nl = 1;
+    for (long long t = m->pushes[which_count]; (t & 1) && nl < LB_LEVELS; t >>= 1) ++nl;
+    m->pushes[which_count] += 1;
     meas_commit_kernel<<<blocks, 256, 0, c->st>>>(m->res, m->off[OBS_COUNT], o0, o1, c->B, m->acc, which_count,
-                                                  m->off[OBS_COUNT]);
+                                                  m->off[OBS_COUNT], m->lb_pend, m->lb_acc, nl);
     count_launch();
     return cudaGetLastError();
 }
@@ -208,6 +239,8 @@ int32_t dqmc_set_lattice(dqmc_ctx* c, int32_t n_bravais, int32_t n_basis, const 
     CK(c, dalloc(c, &m->thop, (size_t)c->ms));
     CK(c, dalloc(c, &m->res, (size_t)c->B * o));
     CK(c, dalloc(c, &m->acc, (size_t)2 + 2 * o));
+    CK(c, dalloc(c, &m->lb_pend, (size_t)c->B * LB_LEVELS * o));
+    CK(c, dalloc(c, &m->lb_acc, (size_t)2 * LB_LEVELS + (size_t)2 * LB_LEVELS * o));
     CK(c, cudaMemcpyAsync(m->s2d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
     CK(c, h2d_mats(c, m->thop, hopping_matrix, 1));
     if ((size_t)4 * n_bravais * sizeof(double) > 48 * 1024)
@@ -286,6 +319,29 @@ int32_t dqmc_measurement_buffer(dqmc_ctx* c, void** device_ptr, int64_t* n_doubl
     if (!c || !device_ptr || !n_doubles) return DQMC_ERR_INVALID;
     if (!c->meas) FAIL(c, DQMC_ERR_INVALID, "dqmc_measurement_buffer: call dqmc_set_lattice first");
     *device_ptr = c->meas->acc; *n_doubles = 2 + 2 * (int64_t)c->meas->off[OBS_COUNT];
+    return DQMC_OK;
+}
+
+int32_t dqmc_binning_levels(void) { return LB_LEVELS; }
+
+int32_t dqmc_measurement_binning_buffer(dqmc_ctx* c, void** device_ptr, int64_t* n_doubles)
+{
+    if (!c || !device_ptr || !n_doubles) return DQMC_ERR_INVALID;
+    if (!c->meas) FAIL(c, DQMC_ERR_INVALID, "dqmc_measurement_binning_buffer: call dqmc_set_lattice first");
+    *device_ptr = c->meas->lb_acc; *n_doubles = 2 * LB_LEVELS + 2 * (int64_t)LB_LEVELS * c->meas->off[OBS_COUNT];
+    return DQMC_OK;
+}
+
+int32_t dqmc_get_measurement_binning(dqmc_ctx* c, double* counts, double* sum, double* sumsq)
+{
+    ENTER(c);
+    if (!c->meas) FAIL(c, DQMC_ERR_INVALID, "dqmc_get_measurement_binning: call dqmc_set_lattice first");
+    if (!counts || !sum || !sumsq) FAIL(c, DQMC_ERR_INVALID, "dqmc_get_measurement_binning: bad arguments");
+    const size_t len = (size_t)c->meas->off[OBS_COUNT];
+    CK(c, cudaMemcpyAsync(counts, c->meas->lb_acc, 2 * LB_LEVELS * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaMemcpyAsync(sum, c->meas->lb_acc + 2 * LB_LEVELS, LB_LEVELS * len * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaMemcpyAsync(sumsq, c->meas->lb_acc + 2 * LB_LEVELS + LB_LEVELS * len, LB_LEVELS * len * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(c, cudaStreamSynchronize(c->st));
     return DQMC_OK;
 }
 

@@ -251,6 +251,41 @@ def spin_density_susceptibility(mc, model=None, dir="z"):
     return DeviceMeasurement({"x": "sdxs", "y": "sdys", "z": "sdzs"}[str(dir).lstrip(":")], True)
 
 
+# ---- configuration recorder (src/configurations.jl:12-60) and replay! (DQMC.jl:418-505)
+class ConfigRecorder:
+    """ConfigRecorder(rate): every `rate` sweeps after thermalization the configuration of every chain is stored in the
+    reference's compressed form -- the chunks of compress(field) (BitArray(conf .== 1), or two bits per value for the GHQ
+    fields), packed on the device (dqmc_get_conf_packed).  configs[i] is a uint64 array (words, n_chains)."""
+
+    def __init__(self, rate=10):
+        self.rate, self.configs, self.sweeps = int(rate), [], []
+
+    def push(self, mc, sweep):
+        if sweep % self.rate == 0:                      # configurations.jl:30-33
+            self.configs.append(mc.ctx.get_conf_packed())
+            self.sweeps.append(int(sweep))
+
+    def __len__(self):
+        return len(self.configs)
+
+    def __getitem__(self, i):
+        return self.configs[i]
+
+    def __iter__(self):
+        return iter(self.configs)
+
+
+class Discarder:
+    """Discarder (configurations.jl): records nothing."""
+    rate = 0
+
+    def push(self, mc, sweep):
+        pass
+
+    def __len__(self):
+        return 0
+
+
 # ---- updates (updates/local_updates.jl:70-84, updates/global_updates.jl:229-270, updates/scheduler.jl:236-289)
 class LocalSweep:
     is_full_sweep = True
@@ -290,7 +325,7 @@ class DQMC:
     """DQMC(model; beta, delta_tau, safe_mult, thermalization, sweeps, measure_rate, seed, field, ...)."""
 
     def __init__(self, model: HubbardModel, *, seed=-1, field=None, n_chains=1, device=0, chain_offset=0,
-                 delay_block=0, scheduler=None, recalculate=None, **kwargs):
+                 delay_block=0, scheduler=None, recalculate=None, recorder=None, recording_rate=None, **kwargs):
         self.model = model
         self.parameters = DQMCParameters(**kwargs)
         self._rng = np.random.default_rng(None if seed == -1 else seed)
@@ -316,6 +351,9 @@ class DQMC:
             check_propagation_error=self.parameters.check_propagation_error,
             seed=(1234 if seed == -1 else seed), chain_offset=chain_offset, device=device, delay_block=delay_block)
         self.stack = _StackView(self)
+        # DQMC.jl:36-37, 57: recorder = ConfigRecorder, recording_rate = measure_rate
+        self.recorder = recorder if recorder is not None else ConfigRecorder(
+            self.parameters.measure_rate if recording_rate is None else recording_rate)
         self.scheduler = scheduler or SimpleScheduler(LocalSweep())
         self.recalculate = recalculate          # CombinedGreensIterator's recalculate (default 2 safe_mult)
         self.global_accepted = np.zeros(n_chains, dtype=np.int64)
@@ -437,14 +475,35 @@ def run(mc: DQMC, *, verbose=False, min_update_rate=0.001):
     while mc.last_sweep < total:
         mc.sweep_once()
         i = mc.last_sweep
-        # sweep_once! (DQMC.jl:200-225): measurements fire on last_sweep % measure_rate == 0 after thermalization
-        if i > p.thermalization and i % p.measure_rate == 0 and mc.measurements:
-            mc.measure()
+        # sweep_once! (DQMC.jl:200-225): after thermalization the configuration goes to the recorder and the measurements
+        # fire on last_sweep % measure_rate == 0
+        if i > p.thermalization:
+            mc.recorder.push(mc, i)
+            if i % p.measure_rate == 0 and mc.measurements:
+                mc.measure()
         if i > min_sweeps and mc.max_acceptance() < min_update_rate:          # DQMC.jl:294-307, every sweep
             mc.sync_field()
             return "CANCELLED_LOW_ACCEPTANCE"                                   # helpers.jl:17-22
         if verbose and i % p.print_rate == 0:
             print(f"\t{i}\n\t\tsweep dur: {(time.time() - t0) / i:.3f}s\n\t\tacc rate (local): {mc.max_acceptance():.3f}")
+    mc.sync_field()
+    return "SUCCESS"
+
+
+def replay(mc: DQMC, configurations=None, *, measure_rate=1):
+    """replay!(mc, configurations = mc.recorder; measure_rate = 1) (DQMC.jl:418-505): every measure_rate-th recorded
+    configuration is decompressed on the device (dqmc_set_conf_packed), the stack and G(0) are rebuilt from it
+    (calculate_greens(mc, 0) -- here reverse_build_stack + propagate, which also leaves a valid stack for the
+    unequal-time measurements) and every measurement is applied."""
+    configurations = mc.recorder if configurations is None else configurations
+    if not mc._initialized:
+        mc.init()
+    for i in range(0, len(configurations), int(measure_rate)):
+        mc.ctx.set_conf_packed(configurations[i])
+        mc.ctx.build_stack()
+        if mc.measurements:
+            mc.measure()
+        mc.last_sweep = i + 1
     mc.sync_field()
     return "SUCCESS"
 

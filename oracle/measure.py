@@ -135,3 +135,34 @@ def time_integral(G00, triples, delta_tau, M, s2d, nbasis):
         for name, fn in PAIR_KERNELS.items():
             out[name + "s"] += w * each_site_pair_by_distance(fn(G00, G0l, Gl0, Gll, l), s2d, nbasis)
     return out
+
+
+class LogBinner:
+    """numpy restatement of BinningAnalysis.jl 0.6's LogBinner (`_push!`: every value that reaches a level is added to that
+    level's {sum, sum of squares, count}; a compressor per level averages two successive values and hands the mean to the
+    next level) -- the accumulator behind every DQMCMeasurement (measurements/generic.jl:62-65, 586-587).  Third-party
+    arithmetic: pinned here only against its definition (level l = statistics of means over 2^l successive values)."""
+
+    def __init__(self, shape=(), levels=20):
+        self.levels = levels
+        self.sum = np.zeros((levels,) + tuple(shape))
+        self.sumsq = np.zeros((levels,) + tuple(shape))
+        self.count = np.zeros(levels, dtype=np.int64)
+        self.pending = [None] * levels
+
+    def push(self, value):
+        v = np.array(value, dtype=np.float64, copy=True)
+        for l in range(self.levels):
+            self.sum[l] += v
+            self.sumsq[l] += v * v
+            self.count[l] += 1
+            if self.pending[l] is None or l == self.levels - 1:
+                self.pending[l] = v
+                return
+            v = 0.5 * (self.pending[l] + v)
+            self.pending[l] = None
+
+    def std_error(self, level):
+        n = self.count[level]
+        mean = self.sum[level] / n
+        return np.sqrt(np.maximum(self.sumsq[level] / n - mean ** 2, 0.0) / (n - 1))

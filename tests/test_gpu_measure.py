@@ -121,3 +121,67 @@ def test_run_with_device_measurements_and_global_updates(b200):
     # half filling is not enforced at mu != 0, but densities stay physical
     assert np.all(vals["occ"] > -1e-9) and np.all(vals["occ"] < 1 + 1e-9)
     assert np.isfinite(mc["SDSz"].mean()).all() and np.isfinite(mc["CDC"].std_error()).all()
+
+
+def test_device_log_binning_matches_logbinner(b200):
+    """The per-level {count, sum, sum of squares} the device keeps for every observable element equal a LogBinner per chain
+    (oracle/measure.py) fed with the values of each measurement, summed over the chains ("per log-bin level")."""
+    from oracle.measure import LogBinner
+    model = b200.HubbardModel(b200.SquareLattice(4), U=-4.0)
+    mc = b200.DQMC(model, beta=1.0, safe_mult=5, seed=5, n_chains=3)
+    mc.init()
+    mc._set_lattice()
+    ctx = mc.ctx
+    binners = None
+    nmeas = 11
+    for k in range(nmeas):
+        ctx.sweep(1)
+        ctx.measure_equal_time()
+        vals = ctx.measurements()
+        if binners is None:
+            binners = {key: [LogBinner(shape=v.shape[1:]) for _ in range(3)] for key, v in vals.items() if key in ("occ", "E", "cdc")}
+        for key, bl in binners.items():
+            for b in range(3):
+                bl[b].push(vals[key][b])
+        if k % 4 == 3:                                          # a TimeIntegral series of its own length
+            ctx.measure_time_integral(5, 0.1)
+    cnt, s, s2 = ctx.measurement_binning()
+    L = cnt.shape[1]
+    want_counts = [3 * (nmeas >> l) for l in range(L)]
+    assert cnt[0].tolist() == want_counts
+    assert cnt[1].tolist() == [3 * (2 >> l) for l in range(L)]
+    for key, bl in binners.items():
+        for l in range(4):
+            assert np.allclose(s[key][l], sum(b.sum[l] for b in bl), rtol=1e-12, atol=1e-13), (key, l)
+            assert np.allclose(s2[key][l], sum(b.sumsq[l] for b in bl), rtol=1e-12, atol=1e-13), (key, l)
+    lv, n, err = ctx.binning_std_errors("E")
+    assert lv.tolist() == [0, 1, 2, 3] and np.all(err[:3] > 0)      # counts are summed over the 3 chains
+    # level 0 is the flat accumulator
+    c_et, c_ti, fs, fs2 = ctx.measurement_stats()
+    assert c_et == cnt[0, 0] and np.allclose(fs["cdc"], s["cdc"][0])
+
+
+@pytest.mark.parametrize("field", [None, "MagneticGHQField"])
+def test_recorder_and_replay(b200, field):
+    """ConfigRecorder + replay! (configurations.jl:12-60, DQMC.jl:418-505): the configurations recorded during run (device
+    bit-packing) replayed on a fresh simulation reproduce every measured value."""
+    def make():
+        model = b200.HubbardModel(b200.SquareLattice(4), U=-4.0)
+        mc = b200.DQMC(model, beta=1.0, safe_mult=5, thermalization=3, sweeps=8, measure_rate=2, seed=9, n_chains=2,
+                       field=field)
+        mc["G"] = b200.greens_measurement(mc, model)
+        mc["E"] = b200.total_energy(mc, model)
+        mc["sdsz"] = b200.spin_density_susceptibility(mc, model, "z")
+        return mc
+    mc = make()
+    assert b200.run(mc) == "SUCCESS"
+    assert len(mc.recorder) == 4 and mc.recorder.sweeps == [4, 6, 8, 10] and mc["G"].count == 4
+    words = (16 * 10 * (2 if field else 1) + 63) // 64
+    assert mc.recorder[0].shape == (words, 2) and mc.recorder[0].dtype == np.uint64
+    mc2 = make()
+    assert b200.replay(mc2, mc.recorder) == "SUCCESS"
+    assert mc2["G"].count == 4
+    assert np.allclose(mc2["G"].mean(), mc["G"].mean(), rtol=0, atol=1e-10)
+    assert np.allclose(mc2["E"].mean(), mc["E"].mean(), rtol=1e-10)
+    assert np.allclose(mc2["sdsz"].mean(), mc["sdsz"].mean(), rtol=1e-8, atol=1e-10)
+    assert np.array_equal(mc2.ctx.get_conf_packed(), mc.recorder[-1])          # the replay ends on the last recorded configuration

@@ -143,3 +143,19 @@ def test_bravais_srctrg2dir():
             trg = (sx + dx) % 3 + 3 * ((sy + dy) % 4)
             assert s2d[src, trg] == shift
     assert np.all(np.diag(s2d) == 0)                        # on-site is direction 1 (0-based 0)
+
+
+def test_log_binner_levels_are_block_means():
+    """LogBinner (BinningAnalysis.jl semantics): level l holds the statistics of the means over 2^l successive values."""
+    from oracle.measure import LogBinner
+    g = np.random.default_rng(0)
+    x = g.normal(size=(37, 3))
+    B = LogBinner(shape=(3,), levels=8)
+    for v in x:
+        B.push(v)
+    for l in range(6):
+        nb = 37 >> l
+        blocks = x[:nb << l].reshape(nb, 1 << l, 3).mean(axis=1)
+        assert B.count[l] == nb
+        assert np.allclose(B.sum[l], blocks.sum(axis=0)) and np.allclose(B.sumsq[l], (blocks ** 2).sum(axis=0))
+    assert B.count[6] == 0
