@@ -304,9 +304,18 @@ def main():
     if world > 1:
         # the path's only collective (final observable reduction) goes through the library's own NCCL communicator
         # on the context's stream; torch.distributed only ships the 128-byte id and does the timing barriers
-        ids = [pkg.Context.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        ctx.comm_init(world, rank, ids[0])
+        # (NCCL announces its version on stdout when a communicator is created: keep stdout for the JSON line)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            ids = [pkg.Context.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            ctx.comm_init(world, rank, ids[0])
+            ctx.reduce_observables()         # first collective of a communicator sets up its connections: not timed
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if world > 1:
