@@ -8,7 +8,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libdqmc_b200.so"
-SOURCES = ["gemm.cu", "udt.cu", "udt_reg.cu", "udt_steps.cu", "rdivp.cu", "update.cu", "update3.cu", "misc.cu", "capi.cu", "ut.cu", "measure.cu", "global.cu"]
+SOURCES = ["gemm.cu", "udt.cu", "udt_reg.cu", "udt_steps.cu", "rdivp.cu", "update.cu", "update3.cu", "slicestep.cu", "misc.cu", "capi.cu", "ut.cu", "measure.cu", "global.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

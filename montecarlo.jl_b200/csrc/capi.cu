@@ -349,11 +349,41 @@ static cudaError_t local_sweep(dqmc_ctx* c, const double* d_unif, const unsigned
 {
     const long long ts = (long long)2 * c->M * c->N;
     const int uf = c->ghq ? 2 : 1;                       // GHQ: Metropolis + choice uniforms per proposal
-    for (int step = 0; step < 2 * c->M; ++step) {
+    for (int step = 0; step < 2 * c->M;) {
         const long long off = (long long)step * c->N;
+        // the propagate after this sweep_spatial is a plain wrap unless the slice closes its range (stack.jl:605-730)
+        auto plain = [&](int slice) {
+            return (c->direction == 1) ? slice != c->rlast[c->current_range - 1] : slice != c->rfirst[c->current_range - 1];
+        };
+        if (c->fused_steps && plain(c->current_slice)) {
+            int run = 0;
+            while (step + run < 2 * c->M && plain(c->current_slice + run * c->direction)) ++run;
+            ProfScope ps(c, DQMC_PROF_UPDATE);
+            SliceStepParams p{};
+            p.n = c->N; p.ld = c->ld; p.nb = c->nb; p.kind = c->kind; p.n_chains = c->B;
+            p.G = c->greens; p.strideG = c->ms;
+            p.conf = c->conf; p.cstride = (long long)c->M * c->N;
+            p.eT2 = c->eT2; p.eT2i = c->eT2i; p.alpha = c->alpha;
+            if (c->ghq) p.ghq = c->ghq_tab;
+            const Scale sp = field_scale(c, 1, 1.0), sn = field_scale(c, 1, -1.0);
+            for (int b = 0; b < 2; ++b)
+                for (int k = 0; k < 4; ++k) { p.lut[0][b][k] = sp.lut[b][k]; p.lut[1][b][k] = sn.lut[b][k]; }
+            p.uniforms = d_unif ? d_unif + uf * off : nullptr; p.ustride = uf * ts; p.uf = uf;
+            p.seed = c->seed; p.sweep_ptr = c->d_sweep_index; p.sweep = c->sweep_index; p.chain0 = c->chain_offset;
+            p.step0 = step; p.nsteps = run; p.slice0 = c->current_slice; p.dir = c->direction;
+            p.check_sign = c->check_sign; p.accepted = c->accepted; p.stats = c->stats_neg;
+            p.forced = d_forced ? d_forced + off : nullptr; p.probs = d_probs ? d_probs + off : nullptr;
+            p.decisions = d_dec ? d_dec + off : nullptr; p.tstride = ts;
+            CE(launch_slice_steps(p, c->st));
+            c->current_slice += run * c->direction;      // what `run` plain propagates do to the state
+            c->generation += run;
+            step += run;
+            continue;
+        }
         CE(sweep_spatial(c, step, d_unif ? d_unif + uf * off : nullptr, uf * ts, d_forced ? d_forced + off : nullptr,
                          d_probs ? d_probs + off : nullptr, d_dec ? d_dec + off : nullptr, ts));
         CE(propagate(c));
+        ++step;
     }
     c->sweep_index += 1;
     bump_kernel<<<1, 1, 0, c->st>>>(c->d_sweep_index);
@@ -502,6 +532,7 @@ int32_t dqmc_create(const dqmc_desc* d, dqmc_ctx** out)
         delete c; g_create_error = "update_variant must be 0 (auto), 1 or 3"; return DQMC_ERR_INVALID;
     }
     c->update_version = d->update_variant ? d->update_variant : (c->N >= 96 ? 3 : 1);
+    c->fused_steps = d->update_variant == 0 && slice_steps_supported(c->N, c->nb);
     t_launch_counter = &c->launches;
     if (c->update_version == 1) {
         c->kb = d->delay_block > 0 ? ((d->delay_block + 3) & ~3) : update_pick_kb(c->N, c->nb);

@@ -176,6 +176,24 @@ int update_pick_kb(int n, int nb);
 cudaError_t launch_update3(const UpdateParams& p, cudaStream_t st);   // submatrix form: G0 + Bc X Br, in-kernel flush
 int update3_pick_kb(int n, int nb);
 
+// ---- small lattices: a run of slice steps (sweep_spatial + wrap) in one kernel, G on chip (slicestep.cu) ----------
+struct SliceStepParams {
+    int n, ld, ldg, nb, kind, n_chains;
+    double* G; long long strideG;            // per matrix
+    int8_t* conf; long long cstride;         // conf of chain 0, slice 1; chain stride
+    const double *eT2, *eT2i;                // exp(-+dtau T), leading dimension ld
+    double alpha, em2a, ep2a;
+    GhqTables ghq;
+    double lut[2][2][4];                     // [e^{+V}, e^{-V}][flavor block][field code]: the Scale look-up tables
+    const double* uniforms; long long ustride; int uf;   // table at the first step (per chain stride), uf * n per step
+    unsigned long long seed; const long long* sweep_ptr; long long sweep; long long chain0;
+    int step0, nsteps, slice0, dir;          // steps step0 .. of the sweep visit slices slice0, slice0 + dir, ...
+    int check_sign; int* accepted; double* stats;
+    const unsigned char* forced; double* probs; unsigned char* decisions; long long tstride;   // at the first step; + n per step
+};
+bool slice_steps_supported(int n, int nb);
+cudaError_t launch_slice_steps(SliceStepParams p, cudaStream_t st);
+
 // ---- small elementwise helpers ---------------------------------------------
 cudaError_t launch_set_identity(double* A, int n, int ld, long long stride, int batch, cudaStream_t st);
 cudaError_t launch_fill(double* v, double val, long long count, cudaStream_t st);

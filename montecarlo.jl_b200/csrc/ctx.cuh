@@ -32,6 +32,7 @@ struct dqmc_ctx {
     double *greens = nullptr, *greens_temp = nullptr, *Ul = nullptr, *Ur = nullptr, *Tl = nullptr, *Tr = nullptr;
     double *tmp1 = nullptr, *tmp2 = nullptr, *curr_U = nullptr, *Dl = nullptr, *Dr = nullptr;
     double* Dgreens = nullptr;         // D of the last Green's function calculation: det(greens) = 1 / prod(Dgreens)
+    bool fused_steps = false;          // n <= 64: runs of slice steps in one kernel (slicestep.cu)
     int update_version = 3;            // 3: update3.cu (n >= 96), 1: update.cu; dqmc_desc.update_variant forces one
     int8_t* conf_backup = nullptr;     // temp_conf of the global updates (fields.jl: temp_conf)
     double *Vwork = nullptr, *tau = nullptr, *udt_scratch = nullptr;
