@@ -335,6 +335,8 @@ cudaError_t launch_udt_reg(const UdtParams& p, cudaStream_t st)
     // (Measured alternative, not kept: compact WY with 32-reflector blocks on the batched DMMA GEMM -- T_b and V_b T_b
     //  from one CTA per block, then W = V_b^T Q, Q -= (V_b T_b) W per block: 1.29 ms per 296 x 256^2 against 0.96 ms here;
     //  the K = 32 updates are bound by re-reading Q, the block preparation by shared-memory traffic.)
+    // (Also measured and not kept: form-Q in the steps kernel's register tiling -- 3-round butterflies, but four times the
+    //  shared-memory reads of the Householder vectors: 1.02 ms against 0.96 ms.)
     DQMC_RPL_SWITCH(rpl, (launch_formq4<R>(p, T4, st)))
     if (err != cudaSuccess) return err;
     // the Val(false) form wants the columns of D^-1 R in pivot (logical) order
