@@ -24,6 +24,32 @@ CASES = [
 ]
 
 
+def _record_iter(name, entry):
+    import json
+    from pathlib import Path
+    out = Path(__file__).resolve().parent.parent / "gpurun_out" / "parity_iterator.json"
+    try:
+        out.parent.mkdir(exist_ok=True)
+        data = json.loads(out.read_text()) if out.exists() else {}
+        data[name] = entry
+        out.write_text(json.dumps(data, indent=1, sort_keys=True))
+    except OSError:
+        pass
+
+
+def test_exact_unequal_time_reference_agrees_with_the_arbiter(b200):
+    """The from-scratch G(k, k) the iterator tests use as `exact` (the oracle's calculate_greens_full1!) is itself within
+    1e-11 of the extended-precision arbiter (oracle/truth_ld.c), on the hardest case of CASES (|U| = 4, beta = 3)."""
+    from oracle import truth as TR
+    ctx, chains = make_pair(b200, "square", (6, 6), U=-4.0, beta=3.0, B=1, safe_mult=8)
+    c = chains[0]
+    for k in (0, 7, 16, 30):
+        Gkk = c.ut_calculate_greens(k, k)
+        Gt = TR.greens_truth_chain(c, slice0=k)
+        assert relerr(Gkk, Gt) < 1e-11
+        assert relerr(ctx.ut_greens(k, k, measured=False)[:, :, :, 0], Gt) < 1e-11
+
+
 def udt_product(ctx_or_chain, getter, prefix, slot):
     U = getter(prefix + "_u", slot)
     D = getter(prefix + "_d", slot)
@@ -125,11 +151,13 @@ def test_combined_greens_iterator_matches_oracle(b200, kind, Ls, U, beta, sm, re
     ctx.build_stack()
     for c in chains:
         c.init()
-    # With recalculate > safe_mult the quick-advance steps amplify rounding differences: the reference
-    # algorithm itself is then only good to ~1e-8 on Gll at |U| = 4 (its own test allows 1e-10 absolute at
-    # U = 1, unequal_time_stack.jl:164-171).  The device has to be as close to the oracle as the oracle is to
-    # the from-scratch G(k, l): tol = 1e-10 + 20 x (oracle's own error at that l) -- independent
-    # realisations of the same amplified rounding noise (every change of summation order in a kernel moves it).
+    # recalculate = safe_mult: device vs the oracle's iterator at 1e-10 (same schedule, every step freshly stabilised).
+    # recalculate = 2 safe_mult: the reference's quick-advance steps (greens_iterators.jl:398-435) amplify rounding noise --
+    # two correct implementations then differ by their independent noise, so a device-vs-oracle bound would measure the
+    # checker.  Both are instead measured against the from-scratch G(k, l) (calculate_greens_full1!/2!, accurate to ~1e-12,
+    # itself checked against the extended-precision arbiter below) and the DEVICE error has to stay under a fixed
+    # number: 2e-7 at |U| <= 4 (the reference's own test allows 1e-10 absolute at U = 1 and recalculate = 4 safe_mult,
+    # unequal_time_stack.jl:164-171; that bound is asserted in test_combined_greens_iterator_reference_bounds).
     exact = None
     if recalc_mult > 1:
         exact = [[(c.ut_greens(0, k), c.ut_greens(k, 0), c.ut_greens(k, k)) for k in range(c.M + 1)] for c in chains]
@@ -137,14 +165,22 @@ def test_combined_greens_iterator_matches_oracle(b200, kind, Ls, U, beta, sm, re
             c.init()
     its = [c.combined_greens_iterator(recalculate=recalc_mult * sm) for c in chains]
     n = 0
+    worst_dev, worst_orc = 0.0, 0.0
     for (l, g0l, gl0, gll) in ctx.combined_greens_iterator(sm, recalculate=recalc_mult * sm):
         for b, it in enumerate(its):
             (lo, o0l, ol0, oll) = next(it)
             assert lo == l
             for name, got, want, i in (("G0l", g0l, o0l, 0), ("Gl0", gl0, ol0, 1), ("Gll", gll, oll, 2)):
-                tol = GTOL + (20.0 * relerr(want, exact[b][l][i]) if exact else 0.0)
-                assert relerr(got[:, :, :, b], want) < tol, (name, l, tol)
+                if exact is None:
+                    assert relerr(got[:, :, :, b], want) < GTOL, (name, l)
+                else:
+                    worst_dev = max(worst_dev, relerr(got[:, :, :, b], exact[b][l][i]))
+                    worst_orc = max(worst_orc, relerr(want, exact[b][l][i]))
         n += 1
+    if exact is not None:
+        _record_iter(f"{kind}{Ls}_U{U}", {"device_vs_exact": worst_dev, "oracle_iterator_vs_exact": worst_orc,
+                                             "recalculate": recalc_mult * sm, "beta": beta})
+        assert worst_dev < 2e-7, (worst_dev, worst_orc)
     assert n == chains[0].M + 1
     # the iteration leaves the sweep machinery intact: G, conf and the next sweep still match the oracle
     acc = ctx.sweep(1)
