@@ -185,7 +185,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         if (lane == 0) g_mbar_arrive(empty0 + 8 * st);   // this warp is done with the slot
     }
 
-    // epilogue: thread owns C[row = g, cols = 2t, 2t+1] of every 8x8 block
+    // epilogue: thread owns C[row = g, cols = 2t, 2t+1] of every 8x8 block.  The column factors are read before the
+    // stores (the compiler cannot hoist them itself: the stores to C might alias the factor vectors).
+    double csv[NJ][2];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int col = n0 + wn0 + j * 8 + 2 * t + e;
+            csv[j][e] = (has_cs && col < p.N) ? scale_at(p.cs, mat, col) : 1.0;
+        }
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
         const int row = m0 + wm0 + i * 8 + g;
@@ -198,7 +207,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 const int col = n0 + wn0 + j * 8 + 2 * t + e;
                 if (col >= p.N) continue;
                 double v = p.alpha * acc[i][j][e] * r;
-                if (has_cs) v *= scale_at(p.cs, mat, col);
+                if (has_cs) v *= csv[j][e];
                 if (p.add_diag && row == col) v += p.add_diag[(long long)mat * p.add_stride + row];
                 double* dst = C + row + (long long)col * p.ldc;
                 if (p.beta != 0.0 && !preload) v += p.beta * (*dst);
@@ -275,7 +284,12 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
     };
     const double w64 = waste(64, 64), w48 = waste(48, 48), w32 = waste(32, 32);
     // Measured on 296 x 256^3: BK = 16 with 4 stages at 3 CTAs/SM 28.98 TFLOP/s, 3 stages 28.44, BK = 32 with 2 stages 28.99,
-    // 2 CTAs/SM 25.2; the cp.async ring this replaces reached 28.4 with 5 CTAs/SM (DMMA pipe 81 % busy either way)
+    // 2 CTAs/SM 25.2; the cp.async ring this replaces reached 28.4 with 5 CTAs/SM (DMMA pipe 81 % busy either way).
+    // profiles/bench_gemm.cu (standalone, 30.5-31.2 on its box; cuBLAS batched = cutlass_80 d884gemm 64x128_16x3, 32 x 64 warp
+    // tiles, 220 registers, 2 CTAs/SM: 33.0): persistent CTAs with a static tile walk 28.3 (lock-step CTAs, no dynamic
+    // balancing); 64 x 128 / 128 x 64 tiles with 32 x 64 warp tiles, with or without the producer warp, 22-26 (two warps per
+    // scheduler do not hide the fragment loads under ptxas' DMMA + NOP schedule); no epilogue stores 29.6 (= no change); an
+    // 8 x longer k loop 33.4 -- the remaining loss is half pipeline fill per 16-k-tile output tile, half the main loop.
     if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4, 3>(p, st);
     if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
     return launch_cfg<32, 32, 16, 16, TA, TB>(p, st);

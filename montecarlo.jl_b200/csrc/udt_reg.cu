@@ -270,13 +270,16 @@ static cudaError_t launch_formq4(const UdtParams& p, double* T4, cudaStream_t st
 bool udt_reg_supported(int n) { UdtLevel g{}; return n <= 288 && udt_steps_geometry(n, g); }
 
 // Level sizes are the sizes at which the geometry gets cheaper: <= 256 needs 4 SMs per matrix (37 matrices
-// in flight), <= 192 two (74: 12 warps of 8 columns x 6 register rows), <= 128 one (148).  Returns the size
+// in flight), <= 192 two (74: 12 warps of 8 columns x 6 register rows), <= 128 one (148), <= 96 half (296).  Returns the size
 // of the trailing block the level that starts with nk columns hands on (0: it finishes the factorisation).
 static int udt_next_level_size(int nk)
 {
     if (nk <= 64) return 0;
-    static const int sizes[4] = {256, 192, 128, 64};
-    for (int k = 0; k < 4; ++k)
+    // (measured, 296 x 256^2: a 224-column level on clusters of 3 -- 48 in flight, 7 waves, 3.4 us per step with 10 fat
+    //  warps -- 0.76 ms for its 32 steps against 0.75 ms on the clusters of 4: no gain; 96 columns fit two matrices per SM:
+    //  128 -> 64 in 0.27 instead of 0.32 ms)
+    static const int sizes[5] = {256, 192, 128, 96, 64};
+    for (int k = 0; k < 5; ++k)
         if (sizes[k] < nk) return sizes[k];
     return 0;
 }

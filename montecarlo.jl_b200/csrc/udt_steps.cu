@@ -249,7 +249,7 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
 
     for (int j = 0; j < jstop; ++j) {
         const int q = j & 1;
-        if (tid == 0) mbar_arrive_expect_tx(xbar0 + 8 * q, tx_bytes);
+        if (CS > 1 && tid == 0) mbar_arrive_expect_tx(xbar0 + 8 * q, tx_bytes);
         // ---- A: best remaining column of the thread -> warp (three REDUX on the order-preserving bit pattern) -----
         double bv = -1.0; int bc = 0x7fffffff;
 #pragma unroll
@@ -293,7 +293,9 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
                     rjj_w = -nu; tau_w = xi1 * copysign(rs_w, nu); inv_w = fast_rcp(xi1);
                 } else reflector_scalars(bv_w, xi1, tau_w, rjj_w, inv_w);
             }
-            double* sb = sendbuf + q * VE;
+            // one CTA per matrix: the entry is written in place and the CTA barrier below publishes it -- no copy engine,
+            // no proxy fence, no mbarrier round trip on the critical path of the step
+            double* sb = (CS > 1) ? sendbuf + q * VE : vbuf + (size_t)q * VE;
             for (int idx = 2 * lane; idx < VB; idx += 64) {
                 const int gg = idx / VP, ii = idx - gg * VP;
                 double2 y = make_double2(0.0, 0.0);
@@ -309,14 +311,16 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
                 *reinterpret_cast<double2*>(sb + VB) = make_double2(live_w ? bv_w : -1.0, (double)bc);
                 *reinterpret_cast<double2*>(sb + VB + 2) = make_double2(tau_w, rjj_w);
             }
-            fence_proxy_async();                         // generic-proxy writes -> visible to the bulk-copy engine
-            __syncwarp();
-            if (lane < CS)
-                bulk_copy_to_peer(mapa_u32(smem_u32(vbuf + ((size_t)q * CS + rank) * VE), (unsigned)lane), smem_u32(sb),
-                                  (unsigned)(VE * 8), mapa_u32(xbar0 + 8 * q, (unsigned)lane));
+            if (CS > 1) {
+                fence_proxy_async();                     // generic-proxy writes -> visible to the bulk-copy engine
+                __syncwarp();
+                if (lane < CS)
+                    bulk_copy_to_peer(mapa_u32(smem_u32(vbuf + ((size_t)q * CS + rank) * VE), (unsigned)lane), smem_u32(sb),
+                                      (unsigned)(VE * 8), mapa_u32(xbar0 + 8 * q, (unsigned)lane));
+            }
         }
         // ---- C: one warp waits for the CS entries of this step, the hardware barrier releases the others ----------
-        if (warp == 0) mbar_wait(xbar0 + 8 * q, (unsigned)(j >> 1) & 1u);
+        if (CS > 1 && warp == 0) mbar_wait(xbar0 + 8 * q, (unsigned)(j >> 1) & 1u);
         __syncthreads();
         // ---- D: cluster winner, identical in every CTA and thread -----------------------------------------
         {

@@ -18,6 +18,13 @@
 //
 // The serial part no longer scales with n, and shared memory holds the factors of ONE flavor at a time, so
 // kb = 44 instead of 24 at n = 256 with two flavors: 6 instead of 11 read-modify-write passes over G.
+//
+// Measured and not kept (round 2): blocks delimited by ACCEPTED flips instead of sites -- the panels only ever hold the
+// accepted columns / rows, so a block can take proposals from a window of up to 64 sites (two diagonal entries per lane)
+// until kb flips are accepted: 5 instead of 8 passes over G at cfg 5, 4-5 instead of 6 at cfg 4.  The serial phase and the
+// X build grow faster than the flush shrinks: cfg 5 (one flavor, 4 x 4 patches on all 256 threads) window 40 / 48 / 56 / 64
+// = 0.624 / 0.640 / 0.640 / 0.680 ms per slice visit; cfg 4 (two flavors: 4 x 8 patches) 0.97 against 0.83 ms.  Smaller
+// blocks lose as well (cfg 4: 36 -> 0.850, 32 -> 0.850, 24 -> 1.04): the kb the host picks is the optimum.
 #include "common.cuh"
 #include "../../include/dqmc_rng.h"
 #include <math.h>
