@@ -31,6 +31,15 @@ struct dqmc_ut {
     double *greens = nullptr, *tmp = nullptr, *U = nullptr, *D = nullptr, *T = nullptr;   // :21-26
     double *s1 = nullptr, *s2 = nullptr, *dv = nullptr;     // scratch (out-of-place products, D copies)
     long long last_update = -1; int last_k = -1, last_l = -1;
+    // Blocks the reference recomputes but whose inputs have not changed (same configuration, same arguments): kept as
+    // copies and restored -- the kernels are deterministic, so a restored block is bit-identical to a recomputed one.
+    //   inverse chain of compute_inverse_udt_block: the state after range `inv_upper` of a chain that started at range
+    //   `inv_lower` (a longer chain with the same start resumes from it: the iterator's recalculations at l = 20, 40, ...
+    //   all start at 0); forward block of slice 0 (every recalculation needs it twice); backward block of the last slice.
+    long long cache_gen = -1;
+    int inv_lower = 0, inv_upper = -1; double *cU = nullptr, *cD = nullptr, *cT = nullptr;
+    bool f0_valid = false; double *f0U = nullptr, *f0D = nullptr, *f0T = nullptr;
+    int b_slice = -1; double *bU = nullptr, *bD = nullptr, *bT = nullptr;
     // CombinedGreensIterator
     bool it_active = false; int it_recalc = 0, it_start = 0, it_stop = 0, it_safe_mult = 0, it_next = 0;
     const double *out_G0l = nullptr, *out_Gl0 = nullptr, *out_Gll = nullptr;
@@ -78,6 +87,9 @@ static cudaError_t ut_get(dqmc_ctx* c, dqmc_ut** out)
     CE(dalloc(c, &u->greens, mat)); CE(dalloc(c, &u->tmp, mat)); CE(dalloc(c, &u->U, mat)); CE(dalloc(c, &u->T, mat));
     CE(dalloc(c, &u->s1, mat)); CE(dalloc(c, &u->s2, mat));
     CE(dalloc(c, &u->D, vec)); CE(dalloc(c, &u->dv, vec));
+    CE(dalloc(c, &u->cU, mat)); CE(dalloc(c, &u->cT, mat)); CE(dalloc(c, &u->cD, vec));
+    CE(dalloc(c, &u->f0U, mat)); CE(dalloc(c, &u->f0T, mat)); CE(dalloc(c, &u->f0D, vec));
+    CE(dalloc(c, &u->bU, mat)); CE(dalloc(c, &u->bT, mat)); CE(dalloc(c, &u->bD, vec));
     u->inv_done.assign((size_t)c->C, 0);
     u->forward_idx = 1; u->backward_idx = E - 1;
     CE(ident(c, umat(c, u->fu, 0))); CE(ones(c, uvec(c, u->fd, 0))); CE(ident(c, umat(c, u->ft, 0)));
@@ -115,41 +127,68 @@ static cudaError_t ut_inv_step(dqmc_ctx* c, dqmc_ut* u, int idx)            // :
     return udt(c, src, no_scale(), umat(c, u->iu, idx - 1), uvec(c, u->id, idx - 1), umat(c, u->it, idx - 1), true);
 }
 
-static cudaError_t ut_build_stack(dqmc_ctx* c, dqmc_ut* u)                  // :128-185
+// At (slice 1, direction +1) -- where the reference measures (DQMC.jl:217) -- the equal-time stack has just finished its
+// down sweep: slots 1 .. C hold (B_M ... B_{first slice of range idx + 1})^T, produced by add_slice_sequence_right with
+// the arithmetic of ut_backward_step on the same configuration (slot 0 has been cleared for the up sweep; a sweep_spatial
+// at slice 1 only touches range 1, which none of them contains).  They are copied instead of recomputed; only the
+// backward step of range 1 remains.  Returns the lowest backward index that is available afterwards.
+static cudaError_t ut_adopt_backward_slots(dqmc_ctx* c, dqmc_ut* u, int* backward_idx)
 {
-    for (int idx = 1; idx <= c->C; ++idx) CE(ut_forward_step(c, u, idx));
-    for (int idx = c->C; idx >= 1; --idx) CE(ut_backward_step(c, u, idx));
-    for (int idx = 1; idx <= c->C; ++idx) { CE(ut_inv_step(c, u, idx)); u->inv_done[idx - 1] = 1; }
-    u->forward_idx = c->C + 1; u->backward_idx = 1;
-    u->last_update = c->generation; u->last_k = u->last_l = -1;
+    *backward_idx = c->C + 1;
+    if (!(c->current_slice == 1 && c->direction == 1) || c->C < 2) return cudaSuccess;
+    ProfScope ps(c, DQMC_PROF_OTHER);
+    const size_t mat = (size_t)c->nmat * c->ms * 8, vec = (size_t)c->nmat * c->N * 8;
+    const int cnt = c->C - 1;                               // slots 1 .. C - 1 (slot C is the identity on both sides)
+    CE(cudaMemcpyAsync(umat(c, u->bu, 1), slot_mat(c, c->u_stack, 1), mat * cnt, cudaMemcpyDeviceToDevice, c->st));
+    CE(cudaMemcpyAsync(uvec(c, u->bd, 1), slot_vec(c, c->d_stack, 1), vec * cnt, cudaMemcpyDeviceToDevice, c->st));
+    CE(cudaMemcpyAsync(umat(c, u->bt, 1), slot_mat(c, c->t_stack, 1), mat * cnt, cudaMemcpyDeviceToDevice, c->st));
+    *backward_idx = 2;
     return cudaSuccess;
 }
 
-static void ut_lazy_reset(dqmc_ctx* c, dqmc_ut* u)                          // :209-214
+static void ut_drop_caches(dqmc_ut* u) { u->inv_upper = -1; u->f0_valid = false; u->b_slice = -1; }
+
+static cudaError_t ut_build_stack(dqmc_ctx* c, dqmc_ut* u)                  // :128-185
+{
+    int have = c->C + 1;
+    CE(ut_adopt_backward_slots(c, u, &have));
+    for (int idx = 1; idx <= c->C; ++idx) CE(ut_forward_step(c, u, idx));
+    for (int idx = have - 1; idx >= 1; --idx) CE(ut_backward_step(c, u, idx));
+    for (int idx = 1; idx <= c->C; ++idx) { CE(ut_inv_step(c, u, idx)); u->inv_done[idx - 1] = 1; }
+    u->forward_idx = c->C + 1; u->backward_idx = 1;
+    u->last_update = c->generation; u->last_k = u->last_l = -1;
+    u->cache_gen = c->generation; ut_drop_caches(u);
+    return cudaSuccess;
+}
+
+static cudaError_t ut_lazy_reset(dqmc_ctx* c, dqmc_ut* u)                   // :209-214
 {
     if (u->last_update != c->generation) {
         u->last_update = c->generation;
         std::fill(u->inv_done.begin(), u->inv_done.end(), 0);
-        u->forward_idx = 1; u->backward_idx = c->C + 1;
+        u->forward_idx = 1;
+        CE(ut_adopt_backward_slots(c, u, &u->backward_idx));
     }
+    if (u->cache_gen != c->generation) { u->cache_gen = c->generation; ut_drop_caches(u); }
+    return cudaSuccess;
 }
 static cudaError_t ut_lazy_build_forward(dqmc_ctx* c, dqmc_ut* u, int upto)
 {
-    ut_lazy_reset(c, u);
+    CE(ut_lazy_reset(c, u));
     for (int idx = u->forward_idx; idx <= upto - 1; ++idx) CE(ut_forward_step(c, u, idx));
     u->forward_idx = std::max(upto, u->forward_idx);
     return cudaSuccess;
 }
 static cudaError_t ut_lazy_build_backward(dqmc_ctx* c, dqmc_ut* u, int downto)
 {
-    ut_lazy_reset(c, u);
+    CE(ut_lazy_reset(c, u));
     for (int idx = u->backward_idx - 1; idx >= downto; --idx) CE(ut_backward_step(c, u, idx));
     u->backward_idx = std::min(downto, u->backward_idx);
     return cudaSuccess;
 }
 static cudaError_t ut_lazy_build_inv(dqmc_ctx* c, dqmc_ut* u, int from, int to)
 {
-    ut_lazy_reset(c, u);
+    CE(ut_lazy_reset(c, u));
     for (int idx = from; idx <= to; ++idx) {
         if (u->inv_done[idx - 1]) continue;
         u->inv_done[idx - 1] = 1;
@@ -173,14 +212,25 @@ static cudaError_t compute_inverse_udt_block(dqmc_ctx* c, dqmc_ut* u, int low, i
     const int lower = find_range_with_value(c, low) + 1;
     const int upper = find_range_with_value(c, high + 1) - 1;
     CE(ut_lazy_build_inv(c, u, lower, upper));
-    CE(ident(c, u->U)); CE(ones(c, u->D)); CE(ident(c, u->T));
-    for (int idx = lower; idx <= upper; ++idx) {
+    int first = lower;
+    if (u->inv_upper >= lower && u->inv_lower == lower && u->inv_upper <= upper) {
+        // the chain over the ranges lower .. inv_upper is the saved one: resume behind it
+        CE(copy_mats(c, u->U, u->cU)); CE(copy_vecs(c, u->D, u->cD)); CE(copy_mats(c, u->T, u->cT));
+        first = u->inv_upper + 1;
+    } else {
+        CE(ident(c, u->U)); CE(ones(c, u->D)); CE(ident(c, u->T));
+    }
+    for (int idx = first; idx <= upper; ++idx) {
         // tmp1 = Diagonal(D) (T inv_u) Diagonal(inv_d); tmp2, D, tmp1 = udt(tmp1)
         CE(mul(c, c->tmp1, u->T, false, umat(c, u->iu, idx - 1), false, vec_scale(c, u->D), no_scale(),
                vec_scale(c, uvec(c, u->id, idx - 1))));
         CE(udt(c, c->tmp1, no_scale(), c->tmp2, u->D, c->tmp1, true));
         CE(mul(c, u->s1, c->tmp1, false, umat(c, u->it, idx - 1), false)); std::swap(u->T, u->s1);
         CE(mul(c, u->s1, u->U, false, c->tmp2, false)); std::swap(u->U, u->s1);
+    }
+    if (upper >= lower && (first <= upper || u->inv_lower != lower || u->inv_upper != upper)) {
+        CE(copy_mats(c, u->cU, u->U)); CE(copy_vecs(c, u->cD, u->D)); CE(copy_mats(c, u->cT, u->T));
+        u->inv_lower = lower; u->inv_upper = upper;
     }
     const int lower_slice = (lower <= c->C) ? c->rfirst[lower - 1] : c->rlast[c->C - 1] + 1;
     const int upper_slice = (upper > 0) ? c->rlast[upper - 1] : 0;
@@ -200,13 +250,21 @@ static cudaError_t compute_forward_udt_block(dqmc_ctx* c, dqmc_ut* u, int slice)
 {
     const int idx = std::max(0, find_range_with_value(c, slice) - 1);
     CE(ut_lazy_build_forward(c, u, idx + 1));
+    if (slice == 0 && u->f0_valid) {
+        CE(copy_mats(c, c->Ul, u->f0U)); CE(copy_vecs(c, c->Dl, u->f0D)); return copy_mats(c, c->Tl, u->f0T);
+    }
     const double* src = umat(c, u->fu, idx);
     double* bufs[2] = {c->Tl, u->s1};
     int w = 0;
     const int target = (idx > 0) ? c->rlast[idx - 1] + 1 : 1;
     for (int l = target; l <= slice; ++l) { CE(slice_left(c, bufs[w], src, l)); src = bufs[w]; w ^= 1; }
     CE(udt(c, src, vec_scale(c, uvec(c, u->fd, idx)), c->Ul, c->Dl, c->tmp1, true));
-    return mul(c, c->Tl, c->tmp1, false, umat(c, u->ft, idx), false);
+    CE(mul(c, c->Tl, c->tmp1, false, umat(c, u->ft, idx), false));
+    if (slice == 0) {
+        CE(copy_mats(c, u->f0U, c->Ul)); CE(copy_vecs(c, u->f0D, c->Dl)); CE(copy_mats(c, u->f0T, c->Tl));
+        u->f0_valid = true;
+    }
+    return cudaSuccess;
 }
 
 // :509-533   (Ur Dr Tr)^T = B_M ... B_{slice+1}
@@ -214,13 +272,19 @@ static cudaError_t compute_backward_udt_block(dqmc_ctx* c, dqmc_ut* u, int slice
 {
     const int idx = find_range_with_value(c, slice) + 1;
     CE(ut_lazy_build_backward(c, u, idx));
+    if (u->b_slice == slice) {
+        CE(copy_mats(c, c->Ur, u->bU)); CE(copy_vecs(c, c->Dr, u->bD)); return copy_mats(c, c->Tr, u->bT);
+    }
     const double* src = umat(c, u->bu, idx - 1);
     double* bufs[2] = {c->Tr, u->s1};
     int w = 0;
     const int target = (idx <= c->C) ? c->rfirst[idx - 1] - 1 : c->rlast[c->C - 1];
     for (int l = target; l >= slice + 1; --l) { CE(slice_daggered_left(c, bufs[w], src, l)); src = bufs[w]; w ^= 1; }
     CE(udt(c, src, vec_scale(c, uvec(c, u->bd, idx - 1)), c->Ur, c->Dr, c->tmp1, true));
-    return mul(c, c->Tr, c->tmp1, false, umat(c, u->bt, idx - 1), false);
+    CE(mul(c, c->Tr, c->tmp1, false, umat(c, u->bt, idx - 1), false));
+    CE(copy_mats(c, u->bU, c->Ur)); CE(copy_vecs(c, u->bD, c->Dr)); CE(copy_mats(c, u->bT, c->Tr));
+    u->b_slice = slice;
+    return cudaSuccess;
 }
 
 // :537-618   slice1 >= slice2:  G = [U D T + Ul Dl Tl Tr' Dr Ur']^-1
