@@ -82,16 +82,20 @@ __device__ __forceinline__ void cp_async16_q(void* smem, const void* gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gmem));
 }
 
-template <int RPL>
-__global__ void __launch_bounds__(256)
+// CPW = columns of Q per warp, NW = warps per CTA.  The build uses CPW = 4, NW = 8: half the accumulators of the round-1 layout
+// (8 columns per warp, 224 registers, one CTA per SM), so two CTAs share an SM and four warps per scheduler hide the shuffle
+// trees and the shared-memory reads of the reflectors.
+template <int RPL, int CPW, int NW>
+__global__ void __launch_bounds__(32 * NW, (CPW == 4 && NW == 8) ? 2 : 1)
 udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
 {
     constexpr int NV = RPL * 32;
+    constexpr int CPC = NW * CPW;                        // columns per CTA
     const int n = p.n, ld = p.ld, ldv = p.ldv;
-    const int ctas_per_mat = (n + 63) / 64;
+    const int ctas_per_mat = (n + CPC - 1) / CPC;
     const int mat = blockIdx.x / ctas_per_mat, part_i = blockIdx.x - mat * ctas_per_mat;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int col0 = part_i * 64 + warp * 8;             // this warp owns columns col0 .. col0 + 7
+    const int col0 = part_i * CPC + warp * CPW;          // this warp owns columns col0 .. col0 + CPW - 1
     const double* Vg = p.Vwork + (long long)mat * p.strideV;
     const double* Tg = T4 + (long long)mat * ngroups * 16;
     double* Ug = p.U + (long long)mat * p.strideU;
@@ -105,18 +109,18 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
 #define VS(s_, jj_, r_) vsb[((size_t)(s_) * CH * 4 + (jj_)) * NV + (r_)]
 #define TS(s_, gb_, i_) tsb[((s_) * CH + (gb_)) * 16 + (i_)]
 
-    double a[8][RPL];
+    double a[CPW][RPL];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
+    for (int c = 0; c < CPW; ++c)
 #pragma unroll
         for (int r = 0; r < RPL; ++r) a[c][r] = (col0 + c < n && lane + 32 * r == col0 + c) ? 1.0 : 0.0;
 
-    const int ctop = min(n, part_i * 64 + 64) - 1;       // highest column of this CTA
+    const int ctop = min(n, part_i * CPC + CPC) - 1;     // highest column of this CTA
     const int gtop = ctop >> 2;
-    const int wtop = (col0 < n) ? (min(n - 1, col0 + 7) >> 2) : -1;   // highest block that touches this warp
+    const int wtop = (col0 < n) ? (min(n - 1, col0 + CPW - 1) >> 2) : -1;   // highest block that touches this warp
     const bool dense = (ldv == NV);
     auto stage = [&](int cidx, int s) {                  // blocks CH cidx .. CH cidx + CH - 1 -> stage s
-        for (int e = tid; e < CH * 4 * (NV / 2); e += 256) {
+        for (int e = tid; e < CH * 4 * (NV / 2); e += 32 * NW) {
             const int jj = e / (NV / 2), r2 = (e - jj * (NV / 2)) * 2;
             const int k = CH * 4 * cidx + jj;
             if (k < n && (dense || r2 + 1 < ldv)) cp_async16_q(&VS(s, jj, r2), Vg + (long long)k * ldv + r2);
@@ -141,12 +145,12 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
         const int g = CH * cidx + gb;
         if (g > gtop || g > wtop) continue;              // warp-uniform
         const int r0 = (4 * g) >> 5;                     // first register row a reflector of this block touches
-        // ---- W = V^T A: 32 independent chains ---------------------------------------------------
-        double d[4][8];
+        // ---- W = V^T A: 4 CPW independent chains ------------------------------------------------
+        double d[4][CPW];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) d[j][c] = 0.0;
+            for (int c = 0; c < CPW; ++c) d[j][c] = 0.0;
 #pragma unroll
         for (int r = 0; r < RPL; ++r)
             if (r >= r0) {
@@ -154,34 +158,54 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
                 for (int j = 0; j < 4; ++j) {
                     const double v = VS(s, gb * 4 + j, lane + 32 * r);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) d[j][c] = fma(v, a[c][r], d[j][c]);
+                    for (int c = 0; c < CPW; ++c) d[j][c] = fma(v, a[c][r], d[j][c]);
                 }
             }
         // ---- one reduction tree for the whole block: halve over the columns, butterfly over the rest --
-        double y1[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double send = h16 ? d[j][c] : d[j][c + 4];
-                const double keep = h16 ? d[j][c + 4] : d[j][c];
-                y1[j][c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-        double y2[4][2];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const double send = h8 ? y1[j][c] : y1[j][c + 2];
-                const double keep = h8 ? y1[j][c + 2] : y1[j][c];
-                y2[j][c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
         double w[4];
+        if constexpr (CPW == 8) {
+            double y1[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double send = h4 ? y2[j][0] : y2[j][1];
-            const double keep = h4 ? y2[j][1] : y2[j][0];
-            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double send = h16 ? d[j][c] : d[j][c + 4];
+                    const double keep = h16 ? d[j][c + 4] : d[j][c];
+                    y1[j][c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            double y2[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const double send = h8 ? y1[j][c] : y1[j][c + 2];
+                    const double keep = h8 ? y1[j][c + 2] : y1[j][c];
+                    y2[j][c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double send = h4 ? y2[j][0] : y2[j][1];
+                const double keep = h4 ? y2[j][1] : y2[j][0];
+                w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+        } else {
+            double y1[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const double send = h16 ? d[j][c] : d[j][c + 2];
+                    const double keep = h16 ? d[j][c + 2] : d[j][c];
+                    y1[j][c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double send = h8 ? y1[j][0] : y1[j][1];
+                const double keep = h8 ? y1[j][1] : y1[j][0];
+                w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] += __shfl_xor_sync(0xffffffffu, w[j], 4);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) w[j] += __shfl_xor_sync(0xffffffffu, w[j], 2);
@@ -198,12 +222,13 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
         }
         // ---- A -= V Y, four columns at a time (register budget) ------------------------------------
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < CPW / 4; ++half) {
             double yy[4][4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int cc = half * 4 + c;
-                const int src = ((cc & 4) ? 16 : 0) | ((cc & 2) ? 8 : 0) | ((cc & 1) ? 4 : 0);
+                const int src = (CPW == 8) ? (((cc & 4) ? 16 : 0) | ((cc & 2) ? 8 : 0) | ((cc & 1) ? 4 : 0))
+                                           : (((cc & 2) ? 16 : 0) | ((cc & 1) ? 8 : 0));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) yy[j][c] = -__shfl_sync(0xffffffffu, y[j], src);
             }
@@ -221,7 +246,7 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
       }
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < CPW; ++c) {
         const int col = col0 + c;
         if (col < n) {
 #pragma unroll
@@ -238,7 +263,7 @@ udt_formq4_kernel(const UdtParams p, const double* __restrict__ T4, int ngroups)
 // ================================================================================================
 // host side
 // ================================================================================================
-template <int RPL>
+template <int RPL, int CPW, int NW>
 static cudaError_t launch_formq4(const UdtParams& p, double* T4, cudaStream_t st)
 {
     const int ngroups = (p.n + 3) / 4;
@@ -247,15 +272,15 @@ static cudaError_t launch_formq4(const UdtParams& p, double* T4, cudaStream_t st
     udt_wy_t_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(p, T4, ngroups);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const int ctas = p.batch * ((p.n + 63) / 64);
+    const int ctas = p.batch * ((p.n + NW * CPW - 1) / (NW * CPW));
     count_launch();
     constexpr int smem = (2 * 4 * 4 * RPL * 32 + 2 * 4 * 16) * (int)sizeof(double);
     // (Q held in the DMMA accumulator layout with the update as one DMMA per 8 rows was measured SLOWER: 1.38 vs
     //  0.96 ms per 296 x 256^2 -- see DESIGN.md; it is not part of the build)
     static SmemAttr attr;
-    e = attr.ensure(udt_formq4_kernel<RPL>, smem);
+    e = attr.ensure(udt_formq4_kernel<RPL, CPW, NW>, smem);
     if (e != cudaSuccess) return e;
-    udt_formq4_kernel<RPL><<<(unsigned)ctas, 256, smem, st>>>(p, T4, ngroups);
+    udt_formq4_kernel<RPL, CPW, NW><<<(unsigned)ctas, 32 * NW, smem, st>>>(p, T4, ngroups);
     return cudaGetLastError();
 }
 
@@ -340,7 +365,9 @@ cudaError_t launch_udt_reg(const UdtParams& p, cudaStream_t st)
     //  the K = 32 updates are bound by re-reading Q, the block preparation by shared-memory traffic.)
     // (Also measured and not kept: form-Q in the steps kernel's register tiling -- 3-round butterflies, but four times the
     //  shared-memory reads of the Householder vectors: 1.02 ms against 0.96 ms.)
-    DQMC_RPL_SWITCH(rpl, (launch_formq4<R>(p, T4, st)))
+    // (Measured, 296 x 256^2: 8 columns per warp, one CTA of 8 warps per SM 0.83 ms; 4 columns per warp on two CTAs per SM
+    //  0.68 ms; 4 columns per warp on one CTA of 16 warps 0.74 ms.)
+    DQMC_RPL_SWITCH(rpl, (launch_formq4<R, 4, 8>(p, T4, st)))
     if (err != cudaSuccess) return err;
     // the Val(false) form wants the columns of D^-1 R in pivot (logical) order
     if (!direct_T)
