@@ -293,7 +293,9 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
     // scheduler do not hide the fragment loads under ptxas' DMMA + NOP schedule); no epilogue stores 29.6 (= no change); an
     // 8 x longer k loop 33.4 -- the remaining loss is half pipeline fill per 16-k-tile output tile, half the main loop.
     // With LDS fragment loads and explicitly double-buffered fragments the 64 x 128 tile reaches 26.6, the 64 x 64 tile
-    // without a producer warp 30.0 against 31.0 with it.
+    // without a producer warp 30.0 against 31.0 with it.  With the TMA loads removed (consumers run on stale tiles) 31.45 and,
+    // with the 8 x longer k loop, 33.4: operand delivery is not the limit.  profiles/microbench_dmma_loop.cu: the bare
+    // shared-memory-fed DMMA loop reaches 31.7 with ONE warp per scheduler and 36.9 with two.
     if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4, 3>(p, st);
     if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
     return launch_cfg<32, 32, 16, 16, TA, TB>(p, st);

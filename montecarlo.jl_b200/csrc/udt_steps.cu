@@ -546,7 +546,8 @@ bool udt_steps_geometry(int nk, UdtLevel& g)
             per_sm = std::min(per_sm, (int)((227 * 1024) / (smem + 1024)));
             per_sm = std::min(per_sm, 16);
             if (per_sm < 1) continue;
-            // (measured at n = 256: 16 warps x 1 column per thread 1.51 ms, 8 warps x 2 columns 1.57 ms -- latency bound)
+            // (measured at n = 256: 16 warps x 1 column per thread 1.51 ms, 8 warps x 2 columns 1.57 ms -- latency bound;
+            //  preferring FEWER warps at every level: 256 -> 1.58 vs 1.62, 128 -> 0.180 vs 0.172, n = 144 0.80 vs 0.74 ms per call)
             const double score = (double)per_sm / cs + 1e-3 * w;
             if (score > best_score) {
                 best_score = score;

@@ -65,7 +65,7 @@ template <class F> float timeit(F f)
 template <int MI, int NJ, bool DBUF, bool REGONLY> void run(const char* name, double* out)
 {
     const int iters = 4000;
-    for (int ctas : {2, 4}) {
+    for (int ctas : {1, 2, 3, 4}) {
         float ms = timeit([&] { k_loop<MI, NJ, DBUF, REGONLY><<<148 * ctas, 128>>>(out, iters); });
         double fl = 2.0 * 256 * MI * NJ * 4.0 * iters * 4 * 148 * ctas;
         printf("%-28s MIxNJ=%dx%d ctas/sm=%d : %6.2f TFLOP/s\n", name, MI, NJ, ctas, fl / ms / 1e9);
@@ -82,5 +82,8 @@ int main()
     run<8, 2, false, false>("smem, single", out);
     run<2, 4, false, false>("smem, single", out);
     run<4, 2, true, false>("smem, double", out);
+    run<4, 8, false, true>("registers only", out);
+    run<4, 8, false, false>("smem, single", out);
+    run<4, 8, true, false>("smem, double", out);
     return 0;
 }
