@@ -171,16 +171,44 @@ cudaError_t calculate_greens(dqmc_ctx* c, double* G)
     return cudaSuccess;
 }
 
+// A run of slice-matrix products on one operand: for small lattices one kernel (slicestep.cu), else one GEMM per slice.
+// op 0: dst = B_{first + count - 1} ... B_first src; op 1: daggered, slices first, first - 1, ...; op 2: inverse, descending.
+// Returns the buffer that holds the result (one of bufs[0], bufs[1]; src itself when count == 0).
+cudaError_t slice_chain(dqmc_ctx* c, int op, const double* src, int first, int count, double* bufs[2], const double** out)
+{
+    if (count <= 0) { *out = src; return cudaSuccess; }
+    if (c->fused_steps) {
+        ProfScope ps(c, DQMC_PROF_GEMM);
+        SliceChainParams p{};
+        p.n = c->N; p.ld = c->ld; p.nb = c->nb; p.ghq = c->ghq ? 1 : 0; p.n_mats = c->nmat; p.op = op;
+        p.first = first; p.count = count;
+        p.src = src; p.dst = bufs[0]; p.stride = c->ms;
+        p.conf = c->conf; p.cstride = (long long)c->M * c->N;
+        p.E = (op == 2) ? c->eT2i : c->eT2;
+        const Scale f = field_scale(c, 1, (op == 2) ? -1.0 : 1.0);
+        for (int b = 0; b < 2; ++b)
+            for (int k = 0; k < 4; ++k) p.lut[b][k] = f.lut[b][k];
+        *out = bufs[0];
+        return launch_slice_chain(p, c->st);
+    }
+    int w = 0;
+    for (int i = 0; i < count; ++i) {
+        const int s = (op == 0) ? first + i : first - i;
+        if (op == 0) CE(slice_left(c, bufs[w], src, s));
+        else if (op == 1) CE(slice_daggered_left(c, bufs[w], src, s));
+        else CE(slice_inv_left(c, bufs[w], src, s));
+        src = bufs[w]; w ^= 1;
+    }
+    *out = src;
+    return cudaSuccess;
+}
+
 // add_slice_sequence_left (stack.jl:377-393), idx 1-based
 static cudaError_t add_slice_sequence_left(dqmc_ctx* c, int idx)
 {
     const double* src = slot_mat(c, c->u_stack, idx - 1);
     double* bufs[2] = {c->curr_U, c->tmp2};
-    int w = 0;
-    for (int s = c->rfirst[idx - 1]; s <= c->rlast[idx - 1]; ++s) {
-        CE(slice_left(c, bufs[w], src, s));
-        src = bufs[w]; w ^= 1;
-    }
+    CE(slice_chain(c, 0, src, c->rfirst[idx - 1], c->rlast[idx - 1] - c->rfirst[idx - 1] + 1, bufs, &src));
     // tmp1 = curr_U * Diagonal(d_stack[idx]) is fused into the QR load
     CE(udt(c, src, vec_scale(c, slot_vec(c, c->d_stack, idx - 1)), slot_mat(c, c->u_stack, idx),
            slot_vec(c, c->d_stack, idx), c->tmp1, true));
@@ -192,11 +220,7 @@ static cudaError_t add_slice_sequence_right(dqmc_ctx* c, int idx)
 {
     const double* src = slot_mat(c, c->u_stack, idx);
     double* bufs[2] = {c->curr_U, c->tmp2};
-    int w = 0;
-    for (int s = c->rlast[idx - 1]; s >= c->rfirst[idx - 1]; --s) {
-        CE(slice_daggered_left(c, bufs[w], src, s));
-        src = bufs[w]; w ^= 1;
-    }
+    CE(slice_chain(c, 1, src, c->rlast[idx - 1], c->rlast[idx - 1] - c->rfirst[idx - 1] + 1, bufs, &src));
     CE(udt(c, src, vec_scale(c, slot_vec(c, c->d_stack, idx)), slot_mat(c, c->u_stack, idx - 1),
            slot_vec(c, c->d_stack, idx - 1), c->tmp1, true));
     return mm(c, slot_mat(c, c->t_stack, idx - 1), c->tmp1, false, false, slot_mat(c, c->t_stack, idx), false, false);

@@ -192,6 +192,16 @@ struct SliceStepParams {
     const unsigned char* forced; double* probs; unsigned char* decisions; long long tstride;   // at the first step; + n per step
 };
 bool slice_steps_supported(int n, int nb);
+// a run of slice-matrix products on one operand per matrix (slicestep.cu): op 0 eT2 e^V M (slices ascending), 1 e^V eT2^T M,
+// 2 e^-V eT2^-1 M (slices descending); src == nullptr starts from the identity
+struct SliceChainParams {
+    int n, ld, ldg, nb, ghq, n_mats, op, first, count;
+    const double* src; double* dst; long long stride;    // per matrix
+    const int8_t* conf; long long cstride;               // conf of chain 0, slice 1; chain stride
+    const double* E;                                     // eT2 (op 0, 1) or eT2^-1 (op 2), leading dimension ld
+    double lut[2][4];                                    // diagonal factor per flavor block and field code
+};
+cudaError_t launch_slice_chain(SliceChainParams p, cudaStream_t st);
 cudaError_t launch_slice_steps(SliceStepParams p, cudaStream_t st);
 
 // ---- small elementwise helpers ---------------------------------------------

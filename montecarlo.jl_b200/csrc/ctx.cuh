@@ -126,6 +126,7 @@ cudaError_t slice_right(dqmc_ctx* c, double* dst, const double* src, int slice);
 cudaError_t slice_inv_right(dqmc_ctx* c, double* dst, const double* src, int slice);
 cudaError_t slice_inv_left(dqmc_ctx* c, double* dst, const double* src, int slice);
 cudaError_t slice_daggered_left(dqmc_ctx* c, double* dst, const double* src, int slice);
+cudaError_t slice_chain(dqmc_ctx* c, int op, const double* src, int first, int count, double* bufs[2], const double** out);
 cudaError_t wrap_greens(dqmc_ctx* c, double* gf, double* tmp, int curr_slice, int direction);
 cudaError_t udt(dqmc_ctx* c, const double* A, Scale colscale, double* U, double* D, double* T, bool apply_pivot);
 cudaError_t rdivp(dqmc_ctx* c, double* A, const double* T, double* work);

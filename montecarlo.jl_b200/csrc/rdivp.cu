@@ -8,6 +8,13 @@
 // the 32 x 32 diagonal blocks are solved by substitution, one thread per row with the
 // row of the panel held in registers and the diagonal block in shared memory.
 // Same operation order per row as the reference (subtract, then divide by T[j,j]).
+//
+// Measured and not kept (round 2): ONE kernel per call -- X = A[:, pivot] T^-1 is independent per row of A, so a CTA of
+// four warps owned 32 rows for the whole substitution (row block gathered through the pivot into shared memory, DMMA for
+// the off-diagonal part of each panel with T read through L1 / L2, the diagonal block solved by one warp).  1.08 ms against
+// 0.47 ms for the 17 launches here: the eight panels become one dependent chain per CTA (gather -> 8 x (DMMA k loop on
+// L2 latency -> 32 divisions in sequence)) at two CTAs per SM, while the per-panel launches run every row of every matrix
+// of the batch at once.
 #include "common.cuh"
 
 namespace dqmc {

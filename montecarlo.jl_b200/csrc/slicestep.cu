@@ -41,6 +41,7 @@ static inline int ss_ld(int n) { return n + (((4 - n) % 16) + 16) % 16; }   // =
 
 // C (n x n, column-major, ldc) = diag(rs) * A * diag(ks) * B * diag(cs); A, B column-major in shared or global memory.
 // 8 warps: warp w owns the 16 x 32 block at rows (w & 3) * 16, columns (w >> 2) * 32; out-of-range parts are skipped.
+template <bool TA = false>
 __device__ __forceinline__ void ss_mm(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda,
                                       const double* __restrict__ B, int ldb, int n, const double* __restrict__ ks,
                                       const double* __restrict__ rs, const double* __restrict__ cs)
@@ -62,7 +63,7 @@ __device__ __forceinline__ void ss_mm(double* __restrict__ C, int ldc, const dou
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int r = wm + 8 * i + g;
-            af[i] = (kok && r < n) ? A[r + (size_t)k * lda] : 0.0;
+            af[i] = (kok && r < n) ? (TA ? A[k + (size_t)r * lda] : A[r + (size_t)k * lda]) : 0.0;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -98,9 +99,9 @@ slice_steps_kernel(const SliceStepParams p)
     const int chain = blockIdx.x;
     double* Gs = sm;                                     // [NB][n][ldg]
     double* Ts = Gs + (size_t)NB * n * ldg;              // [n][ldg] wrap intermediate (one flavor at a time)
-    double* IG = Ts + (size_t)n * ldg;                   // [NB][n]  e_i - G[:, i]
-    double* gr = IG + NB * n;                            // [NB][n]  (Delta / R) G[i, :]
-    double* dpos = gr + NB * n;                          // [NB][n]  e^{+V} of the wrap slice
+    double* IG = Ts + (size_t)n * ldg;                   // [2][n]  e_i - G[:, i]      (one flavor: double buffered by the
+    double* gr = IG + 2 * n;                             // [2][n]  (Delta / R) G[i, :] parity of the accept; two: per flavor)
+    double* dpos = gr + 2 * n;                           // [NB][n]  e^{+V} of the wrap slice
     double* dneg = dpos + NB * n;                        // [NB][n]  e^{-V}
     double* su = dneg + NB * n;                          // [n] Metropolis uniforms of the step
     int8_t* sconf = (int8_t*)(su + n);                   // [n]
@@ -122,7 +123,7 @@ slice_steps_kernel(const SliceStepParams p)
             for (int col = ocol0; col < n; col += cstep)
                 Gs[((size_t)b * n + col) * ldg + orow] = G[(long long)b * p.strideG + orow + (long long)col * p.ld];
     int accepted = 0;
-    double neg_cnt = 0.0, neg_sum = 0.0, neg_min = INFINITY, neg_max = -INFINITY;   // thread 0
+    double neg_cnt = 0.0, neg_sum = 0.0, neg_min = INFINITY, neg_max = -INFINITY;   // thread 0 (one flavor: lanes of warp 0)
 
     for (int s = 0; s < p.nsteps; ++s) {
         const int l = p.slice0 + s * p.dir;              // 1-based slice of this step
@@ -142,6 +143,128 @@ slice_steps_kernel(const SliceStepParams p)
             } else sxnew[i] = (int8_t)(-x);
         }
         __syncthreads();
+        if constexpr (NB == 1) {
+        // ---- sweep_spatial, one flavor block: G in REGISTERS (one 4 x 4 patch per thread, n <= 64) --------------------
+        // Every lane of every warp tracks the diagonal entries of the sites lane and lane + 32 and evaluates all remaining
+        // proposals at once against the current diagonal: up to the first accepted one these are exactly the sequential
+        // decisions (a rejected proposal changes nothing), so (site, Delta / R) of an accept are known to all threads
+        // without a broadcast and an accept costs ONE CTA barrier and 16 FMAs per thread (the shared-memory form above:
+        // two barriers and 48 shared-memory accesses per thread).  The patches go back to Gs for the wrap.
+        const int NPB = (n + 3) >> 2;
+        const bool owner = tid < NPB * NPB;
+        const int oxb = (tid % NPB) * 4, oyb = (tid / NPB) * 4;
+        const int lane = tid & 31, warp = tid >> 5;
+        double g[4][4];
+#pragma unroll
+        for (int iy = 0; iy < 4; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < 4; ++ix) {
+                const int x = oxb + ix, y = oyb + iy;
+                g[ix][iy] = (owner && x < n && y < n) ? Gs[(size_t)y * ldg + x] : 0.0;
+            }
+        double gd[2], un[2];
+        Proposal pr[2];
+        int fc[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = lane + 32 * h;
+            const bool in = j < n;
+            pr[h] = make_proposal(p.kind, in ? (int)sconf[j] : 1, in ? (int)sxnew[j] : 1, p.ghq, em2a, ep2a);
+            un[h] = in ? su[j] : 2.0;
+            fc[h] = (in && p.forced) ? (int)p.forced[toff + j] : -1;
+            gd[h] = in ? Gs[(size_t)j * ldg + j] : 0.0;
+        }
+        int k = 0, next = 0;
+        for (;;) {
+            double prob[2], cf[2];
+            int acc[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = lane + 32 * h;
+                const bool elig = (j >= next) && (j < n);
+                const double Rv = 1.0 + pr[h].Dl[0] * (1.0 - gd[h]);
+                cf[h] = pr[h].Dl[0] * ss_rcp(Rv);                    // Delta / R, speculative
+                prob[h] = proposal_prob(p.kind, pr[h], Rv * Rv);
+                const int a_ = (fc[h] >= 0) ? (fc[h] != 0) : ((prob[h] > 1.0) || (un[h] < prob[h]));
+                acc[h] = elig ? a_ : 0;
+            }
+            const unsigned b0 = __ballot_sync(0xffffffffu, acc[0]);
+            const unsigned b1 = __ballot_sync(0xffffffffu, acc[1]);
+            const int jacc = b0 ? (__ffs(b0) - 1) : (b1 ? 32 + __ffs(b1) - 1 : -1);
+            if (warp == 0) {                                 // traces and statistics of the real decisions
+                const int jlast = (jacc >= 0) ? jacc : n - 1;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = lane + 32 * h;
+                    if (j >= next && j <= jlast) {
+                        if (p.check_sign && prob[h] < 0.0) {
+                            neg_cnt += 1.0; neg_sum += log10(fabs(prob[h]));
+                            neg_min = fmin(neg_min, prob[h]); neg_max = fmax(neg_max, prob[h]);
+                        }
+                        if (p.probs) p.probs[toff + j] = prob[h];
+                        if (p.decisions) p.decisions[toff + j] = (unsigned char)(j == jacc);
+                    }
+                }
+            }
+            if (jacc < 0) break;
+            const int src = jacc & 31, hh = jacc >> 5;
+            const double c0 = __shfl_sync(0xffffffffu, hh ? cf[1] : cf[0], src);
+            const int j = jacc;
+            if (tid == src) { sconf[j] = sxnew[j]; cl[j] = sxnew[j]; }
+            double* cvb = IG + (k & 1) * n;                  // G[:, j] - e_j   (the reference's -(e_j - G[:, j]))
+            double* rvb = gr + (k & 1) * n;                  // (Delta / R) G[j, :]
+            if (owner) {
+                if (j >= oyb && j < oyb + 4) {               // this patch holds part of column j
+#pragma unroll
+                    for (int ix = 0; ix < 4; ++ix) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int iy = 0; iy < 4; ++iy) v = (oyb + iy == j) ? g[ix][iy] : v;
+                        const int x = oxb + ix;
+                        if (x < n) cvb[x] = v - ((x == j) ? 1.0 : 0.0);
+                    }
+                }
+                if (j >= oxb && j < oxb + 4) {               // ... part of row j
+#pragma unroll
+                    for (int iy = 0; iy < 4; ++iy) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int ix = 0; ix < 4; ++ix) v = (oxb + ix == j) ? g[ix][iy] : v;
+                        const int y = oyb + iy;
+                        if (y < n) rvb[y] = c0 * v;
+                    }
+                }
+            }
+            __syncthreads();
+            if (owner) {
+                double cv[4], rv[4];
+#pragma unroll
+                for (int ix = 0; ix < 4; ++ix) cv[ix] = (oxb + ix < n) ? cvb[oxb + ix] : 0.0;
+#pragma unroll
+                for (int iy = 0; iy < 4; ++iy) rv[iy] = (oyb + iy < n) ? rvb[oyb + iy] : 0.0;
+#pragma unroll
+                for (int iy = 0; iy < 4; ++iy)
+#pragma unroll
+                    for (int ix = 0; ix < 4; ++ix) g[ix][iy] = fma(cv[ix], rv[iy], g[ix][iy]);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int jj = lane + 32 * h;
+                if (jj < n) gd[h] = fma(cvb[jj], rvb[jj], gd[h]);
+            }
+            ++k; next = j + 1;
+        }
+        accepted += k;
+        if (owner)
+#pragma unroll
+            for (int iy = 0; iy < 4; ++iy)
+#pragma unroll
+                for (int ix = 0; ix < 4; ++ix) {
+                    const int x = oxb + ix, y = oyb + iy;
+                    if (x < n && y < n) Gs[(size_t)y * ldg + x] = g[ix][iy];
+                }
+        __syncthreads();
+        } else {
         // ---- sweep_spatial (local_updates.jl:23-60): decisions taken redundantly by every thread --------------
         for (int i = 0; i < n; ++i) {
             const Proposal pr = make_proposal(p.kind, (int)sconf[i], (int)sxnew[i], p.ghq, em2a, ep2a);
@@ -187,6 +310,7 @@ slice_steps_kernel(const SliceStepParams p)
                 __syncthreads();
             }
         }
+        }
         // ---- wrap_greens! to the next slice (stack.jl:594-603) -------------------------------------------------------
         const int lw = (p.dir == 1) ? l : l - 1;         // slice whose B matrix wraps: B_l going up, B_{l-1} going down
         const int8_t* cw = conf + (long long)(lw - 1) * n;
@@ -220,6 +344,14 @@ slice_steps_kernel(const SliceStepParams p)
         for (int b = 0; b < NB; ++b)
             for (int col = ocol0; col < n; col += cstep)
                 G[(long long)b * p.strideG + orow + (long long)col * p.ld] = Gs[((size_t)b * n + col) * ldg + orow];
+    if (NB == 1 && tid < 32) {                           // the lanes of warp 0 hold the statistics of their own sites
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            neg_cnt += __shfl_xor_sync(0xffffffffu, neg_cnt, o); neg_sum += __shfl_xor_sync(0xffffffffu, neg_sum, o);
+            neg_min = fmin(neg_min, __shfl_xor_sync(0xffffffffu, neg_min, o));
+            neg_max = fmax(neg_max, __shfl_xor_sync(0xffffffffu, neg_max, o));
+        }
+    }
     if (tid == 0) {
         if (p.accepted) p.accepted[chain] += accepted;
         if (p.stats && neg_cnt > 0.0) {
@@ -229,10 +361,70 @@ slice_steps_kernel(const SliceStepParams p)
     }
 }
 
+// ---- a run of slice-matrix products on one operand (small lattices) ---------------------------------------------
+// add_slice_sequence_left / _right (stack.jl:377-416) and the builds of the unequal-time stack multiply one matrix by
+// the slice matrices of a whole range, one GEMM launch per slice; for n <= 64 a launch is a few microseconds of latency
+// for ~0.1 us of tensor work.  Here one CTA per matrix keeps the operand in shared memory and applies the `count` slice
+// matrices back to back (same DMMA order over k as gemm.cu, so the products are bit-identical to the separate launches):
+//   op 0  M <- eT2 e^{V_s} M               multiply_slice_matrix_left!          (slices first, first + 1, ...)
+//   op 1  M <- e^{V_s} eT2^T M             multiply_daggered_slice_matrix_left! (slices first, first - 1, ...)
+//   op 2  M <- e^{-V_s} eT2^-1 M           multiply_slice_matrix_inv_left!      (slices first, first - 1, ...)
+__global__ void __launch_bounds__(256)
+slice_chain_kernel(const SliceChainParams p)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int n = p.n, ldg = p.ldg, tid = threadIdx.x, NT = blockDim.x;
+    const int mat = blockIdx.x, chain = mat / p.nb, blk = mat - chain * p.nb;
+    double* Ma = sm;                                     // [n][ldg]
+    double* Mb = Ma + (size_t)n * ldg;                   // [n][ldg]
+    double* dv = Mb + (size_t)n * ldg;                   // [n] diagonal factor of the current slice
+    const int rp = (n <= 16) ? 16 : ((n <= 32) ? 32 : 64), rsh = (n <= 16) ? 4 : ((n <= 32) ? 5 : 6);
+    const int orow = tid & (rp - 1), ocol0 = tid >> rsh, cstep = NT >> rsh;
+    const bool rok = orow < n;
+    const int8_t* conf = p.conf + (long long)chain * p.cstride;
+    if (p.src) {
+        const double* S = p.src + (long long)mat * p.stride;
+        if (rok) for (int col = ocol0; col < n; col += cstep) Ma[(size_t)col * ldg + orow] = S[orow + (long long)col * p.ld];
+    } else {
+        if (rok) for (int col = ocol0; col < n; col += cstep) Ma[(size_t)col * ldg + orow] = (col == orow) ? 1.0 : 0.0;
+    }
+    double* cur = Ma; double* oth = Mb;
+    for (int i = 0; i < p.count; ++i) {
+        const int s = (p.op == 0) ? p.first + i : p.first - i;      // 1-based slice
+        __syncthreads();                                 // operand complete; dv of the previous slice no longer read
+        if (tid < n) {
+            const int x = conf[(long long)(s - 1) * n + tid];
+            const int code = p.ghq ? ((x - 1) & 3) : ((x > 0) ? 0 : 1);
+            dv[tid] = p.lut[blk][code];
+        }
+        __syncthreads();
+        if (p.op == 0) ss_mm<false>(oth, ldg, p.E, p.ld, cur, ldg, n, dv, nullptr, nullptr);
+        else if (p.op == 1) ss_mm<true>(oth, ldg, p.E, p.ld, cur, ldg, n, nullptr, dv, nullptr);
+        else ss_mm<false>(oth, ldg, p.E, p.ld, cur, ldg, n, nullptr, dv, nullptr);
+        double* t = cur; cur = oth; oth = t;
+    }
+    __syncthreads();
+    double* D = p.dst + (long long)mat * p.stride;
+    if (rok) for (int col = ocol0; col < n; col += cstep) D[orow + (long long)col * p.ld] = cur[(size_t)col * ldg + orow];
+}
+
+cudaError_t launch_slice_chain(SliceChainParams p, cudaStream_t st)
+{
+    if (p.n_mats <= 0) return cudaSuccess;
+    p.ldg = ss_ld(p.n);
+    const size_t smem = ((size_t)2 * p.n * p.ldg + p.n) * sizeof(double);
+    static SmemAttr attr;
+    cudaError_t e = attr.ensure(slice_chain_kernel, smem);
+    if (e != cudaSuccess) return e;
+    slice_chain_kernel<<<(unsigned)p.n_mats, 256, smem, st>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
 static size_t slice_steps_smem(int n, int nb)
 {
     const int ldg = ss_ld(n);
-    return ((size_t)(nb + 1) * n * ldg + (size_t)4 * nb * n + n) * sizeof(double) + 2 * (size_t)n + 16;
+    return ((size_t)(nb + 1) * n * ldg + (size_t)(4 + 2 * nb) * n + n) * sizeof(double) + 2 * (size_t)n + 16;
 }
 
 bool slice_steps_supported(int n, int nb) { return n <= 64 && slice_steps_smem(n, nb) <= 110 * 1024; }

@@ -366,7 +366,7 @@ cudaError_t launch_udt_reg(const UdtParams& p, cudaStream_t st)
     // (Also measured and not kept: form-Q in the steps kernel's register tiling -- 3-round butterflies, but four times the
     //  shared-memory reads of the Householder vectors: 1.02 ms against 0.96 ms.)
     // (Measured, 296 x 256^2: 8 columns per warp, one CTA of 8 warps per SM 0.83 ms; 4 columns per warp on two CTAs per SM
-    //  0.68 ms; 4 columns per warp on one CTA of 16 warps 0.74 ms.)
+    //  0.68 ms; 4 columns per warp on one CTA of 16 warps 0.74 ms; 2 columns per warp on three CTAs per SM 0.86 ms.)
     DQMC_RPL_SWITCH(rpl, (launch_formq4<R, 4, 8>(p, T4, st)))
     if (err != cudaSuccess) return err;
     // the Val(false) form wants the columns of D^-1 R in pivot (logical) order

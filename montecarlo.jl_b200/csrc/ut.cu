@@ -103,8 +103,7 @@ static cudaError_t ut_forward_step(dqmc_ctx* c, dqmc_ut* u, int idx)        // :
 {
     const double* src = umat(c, u->fu, idx - 1);
     double* bufs[2] = {c->curr_U, c->tmp2};
-    int w = 0;
-    for (int s = c->rfirst[idx - 1]; s <= c->rlast[idx - 1]; ++s) { CE(slice_left(c, bufs[w], src, s)); src = bufs[w]; w ^= 1; }
+    CE(slice_chain(c, 0, src, c->rfirst[idx - 1], c->rlast[idx - 1] - c->rfirst[idx - 1] + 1, bufs, &src));
     CE(udt(c, src, vec_scale(c, uvec(c, u->fd, idx - 1)), umat(c, u->fu, idx), uvec(c, u->fd, idx), c->tmp1, true));
     return mul(c, umat(c, u->ft, idx), c->tmp1, false, umat(c, u->ft, idx - 1), false);
 }
@@ -112,18 +111,20 @@ static cudaError_t ut_backward_step(dqmc_ctx* c, dqmc_ut* u, int idx)       // :
 {
     const double* src = umat(c, u->bu, idx);
     double* bufs[2] = {c->curr_U, c->tmp2};
-    int w = 0;
-    for (int s = c->rlast[idx - 1]; s >= c->rfirst[idx - 1]; --s) { CE(slice_daggered_left(c, bufs[w], src, s)); src = bufs[w]; w ^= 1; }
+    CE(slice_chain(c, 1, src, c->rlast[idx - 1], c->rlast[idx - 1] - c->rfirst[idx - 1] + 1, bufs, &src));
     CE(udt(c, src, vec_scale(c, uvec(c, u->bd, idx)), umat(c, u->bu, idx - 1), uvec(c, u->bd, idx - 1), c->tmp1, true));
     return mul(c, umat(c, u->bt, idx - 1), c->tmp1, false, umat(c, u->bt, idx), false);
 }
 static cudaError_t ut_inv_step(dqmc_ctx* c, dqmc_ut* u, int idx)            // :165-174
 {
     double* bufs[2] = {c->curr_U, c->tmp2};
-    CE(ident(c, bufs[0]));
-    const double* src = bufs[0];
-    int w = 1;
-    for (int s = c->rlast[idx - 1]; s >= c->rfirst[idx - 1]; --s) { CE(slice_inv_left(c, bufs[w], src, s)); src = bufs[w]; w ^= 1; }
+    const double* src = nullptr;
+    if (c->fused_steps) {                                // the fused kernel starts from the identity itself
+        CE(slice_chain(c, 2, nullptr, c->rlast[idx - 1], c->rlast[idx - 1] - c->rfirst[idx - 1] + 1, bufs, &src));
+    } else {
+        CE(ident(c, bufs[1]));
+        CE(slice_chain(c, 2, bufs[1], c->rlast[idx - 1], c->rlast[idx - 1] - c->rfirst[idx - 1] + 1, bufs, &src));
+    }
     return udt(c, src, no_scale(), umat(c, u->iu, idx - 1), uvec(c, u->id, idx - 1), umat(c, u->it, idx - 1), true);
 }
 
