@@ -295,7 +295,11 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
     // With LDS fragment loads and explicitly double-buffered fragments the 64 x 128 tile reaches 26.6, the 64 x 64 tile
     // without a producer warp 30.0 against 31.0 with it.  With the TMA loads removed (consumers run on stale tiles) 31.45 and,
     // with the 8 x longer k loop, 33.4: operand delivery is not the limit.  profiles/microbench_dmma_loop.cu: the bare
-    // shared-memory-fed DMMA loop reaches 31.7 with ONE warp per scheduler and 36.9 with two.
+    // shared-memory-fed DMMA loop reaches 31.7 with ONE warp per scheduler and 36.9 with two.  Without any mbarrier traffic
+    // either: 32.1 (34.0 with the 8 x longer k loop).  A 64 x 128 tile without producer warp whose slots are re-armed by
+    // the LAST consumer warp to finish them (shared-memory counter, nobody waits): 26.5 as well; compiling the inner
+    // diagonal factor out, constant instead of random operands: no change.  What separates the 64 x 128 kernel (two warps
+    // per scheduler, 72 % of the pipe) from the microbenchmark (99 % with two) was not found.
     if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4, 3>(p, st);
     if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
     return launch_cfg<32, 32, 16, 16, TA, TB>(p, st);
