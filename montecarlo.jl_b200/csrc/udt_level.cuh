@@ -7,9 +7,10 @@ namespace dqmc {
 struct UdtLevel {
     // geometry (filled by udt_steps_geometry)
     int cs;         // CTAs (cluster size) per matrix
-    int cpt;        // columns per thread
+    int cpt;        // register columns per thread
+    int cps;        // columns per thread kept in a shared-memory strip (hybrid geometries; 0 otherwise)
     int rpt;        // rows per thread (rows 8 i + g, i < rpt)
-    int nwarps;     // warps per CTA; a warp owns 4 * cpt local columns
+    int nwarps;     // warps per CTA; a warp owns 4 * (cpt + cps) local columns
     size_t smem;
     // problem
     int n;          // size of this level's (sub)matrix

@@ -176,11 +176,16 @@ __device__ __forceinline__ unsigned long long warp_best(unsigned long long key, 
     return ((unsigned long long)bhi << 32) | blo;
 }
 
-template <int RPT, int CPT>
+// CPS > 0: HYBRID panel.  Besides its CPT register columns a thread owns CPS columns in a private strip of shared memory
+// (row pairs as double2, element (es, pair) of thread tid at ((es * RPT / 2 + pair) * NT + tid): consecutive lanes ->
+// conflict-free LDS.128 / STS.128).  The strips double the panel an SM holds, so a matrix needs half the SMs and twice as
+// many matrices are in flight; a step pays ~3 shared-memory passes over the strips (LSU bound) on top of its latency chain.
+template <int RPT, int CPT, int CPS>
 __global__ void __launch_bounds__(udt_max_threads(RPT, CPT), 1)
 udt_steps_kernel(const UdtParams p, const UdtLevel L)
 {
     static_assert(RPT % 2 == 0, "rows per thread come in LDS.128 pairs");
+    constexpr int CT = CPT + CPS;                        // columns per thread: e < CPT in registers, the rest in the strip
     constexpr int VP = RPT + 2;                          // [g][VP]: 2 VP = 4 (mod 8) words -> conflict-free LDS.128 over g
     constexpr int VB = 8 * VP;                           // doubles per published vector
     cg::cluster_group cluster = cg::this_cluster();
@@ -201,9 +206,15 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
     double* rdia = taus + n;                             // [n]  R_jj
     unsigned long long* wbkey = reinterpret_cast<unsigned long long*>(rdia + n);     // [2][16] per-warp candidates
     unsigned long long* bars = wbkey + 32;               // [0..1] exchange mbarriers
-    int* colstep = (int*)(bars + 2);                     // [nwarps * 4 * CPT]  step at which a local slot was retired (-1: active)
-    int* perm = colstep + nwarps * 4 * CPT;              // [n]
+    int* colstep = (int*)(bars + 2);                     // [nwarps * 4 * CT]  step at which a local slot was retired (-1: active)
+    int* perm = colstep + nwarps * 4 * CT;               // [n]
     int* wbcol = perm + n;                               // [2][16]
+    const int NT = nwarps * 32;
+    // strips: behind the int arrays, 16-byte aligned
+    // (offset arithmetic on the shared base pointer: an integer round trip would turn the strip accesses into generic loads)
+    const size_t strip_off = ((size_t)(reinterpret_cast<const char*>(wbcol + 32) - reinterpret_cast<const char*>(sm)) + 15) & ~(size_t)15;
+    double2* strip = reinterpret_cast<double2*>(reinterpret_cast<char*>(sm) + strip_off) + tid;
+#define STRIP(es_, pair_) strip[(size_t)((es_) * (RPT / 2) + (pair_)) * NT]
     const unsigned xbar0 = smem_u32(bars);
     const unsigned tx_bytes = (unsigned)CS * (unsigned)(VE * 8);
     const float inv_cs = 1.0f / (float)CS;               // exact small-integer division by the cluster size
@@ -215,11 +226,11 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
 
     // ---- load the panel into registers ------------------------------------------------------
     double a[CPT][RPT];
-    double nrm[CPT];
+    double nrm[CT];
     unsigned act = 0;                                    // bit e set <=> column e of this thread is still active
 #pragma unroll
-    for (int e = 0; e < CPT; ++e) {
-        const int s = (warp * CPT + e) * 4 + t;
+    for (int e = 0; e < CT; ++e) {
+        const int s = (warp * CT + e) * 4 + t;
         const bool have = s < nloc;
         const int col = s * CS + rank;
         const double sc = (have && joff == 0 && p.colscale.mode) ? scale_at(p.colscale, mat, col) : 1.0;
@@ -229,7 +240,8 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
             const int r0 = 8 * i + g, r1 = r0 + 8;
             const double x0 = (have && r0 < n) ? Ag[r0 + (long long)col * ld] * sc : 0.0;
             const double x1 = (have && r1 < n) ? Ag[r1 + (long long)col * ld] * sc : 0.0;
-            a[e][i] = x0; a[e][i + 1] = x1;
+            if (e < CPT) { a[e < CPT ? e : 0][i] = x0; a[e < CPT ? e : 0][i + 1] = x1; }
+            else STRIP(e - CPT, i >> 1) = make_double2(x0, x1);
             acc0 = fma(x0, x0, acc0); acc1 = fma(x1, x1, acc1);
         }
         double acc = acc0 + acc1;
@@ -253,8 +265,8 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
         // ---- A: best remaining column of the thread -> warp (three REDUX on the order-preserving bit pattern) -----
         double bv = -1.0; int bc = 0x7fffffff;
 #pragma unroll
-        for (int e = 0; e < CPT; ++e)
-            if ((act >> e) & 1u) cand_merge(bv, bc, nrm[e], ((warp * CPT + e) * 4 + t) * CS + rank);
+        for (int e = 0; e < CT; ++e)
+            if ((act >> e) & 1u) cand_merge(bv, bc, nrm[e], ((warp * CT + e) * 4 + t) * CS + rank);
         const unsigned long long key_w = warp_best(cand_key(bv), bc);     // bc <- column of the warp's best
         const bool live_w = key_w != 0ull;
         const double bv_w = key_value(key_w);
@@ -277,13 +289,14 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
             double tau_w = 0.0, rjj_w = 0.0, inv_w = 0.0;
             if (live_w) {
                 const int sw = (int)((float)(bc - rank) * inv_cs + 0.5f);
-                const int es = (sw >> 2) % CPT, ts = sw & 3;
+                const int es = (sw >> 2) % CT, ts = sw & 3;
 #pragma unroll
-                for (int e = 0; e < CPT; ++e)
+                for (int e = 0; e < CT; ++e)
                     if (e == es && t == ts) {
 #pragma unroll
                         for (int i = 0; i < RPT; i += 2)
-                            *reinterpret_cast<double2*>(wst + g * VP + i) = make_double2(a[e][i], a[e][i + 1]);
+                            *reinterpret_cast<double2*>(wst + g * VP + i) =
+                                (e < CPT) ? make_double2(a[e < CPT ? e : 0][i], a[e < CPT ? e : 0][i + 1]) : STRIP(e - CPT, i >> 1);
                     }
                 __syncwarp();
                 double xi1 = wst[(j & 7) * VP + (j >> 3)];
@@ -344,8 +357,8 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
         if (rank == br) {
             // retire the pivot column; its Householder vector goes to global memory for the Q kernel
             const int s = sglob;                         // bc = s * CS + rank
-            if (warp == s / (4 * CPT) && t == (s & 3)) {
-                act &= ~(1u << ((s >> 2) % CPT));
+            if (warp == s / (4 * CT) && t == (s & 3)) {
+                act &= ~(1u << ((s >> 2) % CT));
                 if (g == 0) colstep[s] = j;
             }
             double* vcol = Vg + (long long)(joff + j) * ldv;
@@ -419,6 +432,74 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
                 d += __shfl_xor_sync(0xffffffffu, d, 16);
                 nrm[e] = d;
             }
+            // ---- the same for the strip columns (shared memory; only compiled for the hybrid geometries) ---------
+            if constexpr (CPS > 0) {
+                double e0[CPS], e1[CPS];
+#pragma unroll
+                for (int es = 0; es < CPS; ++es) e0[es] = e1[es] = 0.0;
+#pragma unroll
+                for (int gi = 0; gi < RPT / GS; ++gi)
+                    if (gi >= gi0) {
+#pragma unroll
+                        for (int i = gi * GS; i < gi * GS + GS; i += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(vb + i);
+#pragma unroll
+                            for (int es = 0; es < CPS; ++es) {
+                                const double2 x = STRIP(es, i >> 1);
+                                e0[es] = fma(v.x, x.x, e0[es]); e1[es] = fma(v.y, x.y, e1[es]);
+                            }
+                        }
+                    }
+                double se[CPS];
+#pragma unroll
+                for (int es = 0; es < CPS; ++es) {
+                    double d = e0[es] + e1[es];
+                    d += __shfl_xor_sync(0xffffffffu, d, 4);
+                    d += __shfl_xor_sync(0xffffffffu, d, 8);
+                    d += __shfl_xor_sync(0xffffffffu, d, 16);
+                    se[es] = ((act >> (CPT + es)) & 1u) ? -tau * d : 0.0;
+                }
+#pragma unroll
+                for (int es = 0; es < CPS; ++es) e0[es] = e1[es] = 0.0;
+#pragma unroll
+                for (int gi = 0; gi < RPT / GS; ++gi) {
+                    if (gi > gi0) {
+#pragma unroll
+                        for (int i = gi * GS; i < gi * GS + GS; i += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(vb + i);
+#pragma unroll
+                            for (int es = 0; es < CPS; ++es) {
+                                double2 x = STRIP(es, i >> 1);
+                                x.x = fma(v.x, se[es], x.x); x.y = fma(v.y, se[es], x.y);
+                                STRIP(es, i >> 1) = x;
+                                e0[es] = fma(x.x, x.x, e0[es]); e1[es] = fma(x.y, x.y, e1[es]);
+                            }
+                        }
+                    } else if (gi == gi0) {
+#pragma unroll
+                        for (int i = gi * GS; i < gi * GS + GS; i += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(vb + i);
+                            const bool k0 = 8 * i + g > j, k1 = 8 * i + 8 + g > j;
+#pragma unroll
+                            for (int es = 0; es < CPS; ++es) {
+                                double2 x = STRIP(es, i >> 1);
+                                x.x = fma(v.x, se[es], x.x); x.y = fma(v.y, se[es], x.y);
+                                STRIP(es, i >> 1) = x;
+                                const double m0 = k0 ? x.x : 0.0, m1 = k1 ? x.y : 0.0;
+                                e0[es] = fma(m0, m0, e0[es]); e1[es] = fma(m1, m1, e1[es]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int es = 0; es < CPS; ++es) {
+                    double d = e0[es] + e1[es];
+                    d += __shfl_xor_sync(0xffffffffu, d, 4);
+                    d += __shfl_xor_sync(0xffffffffu, d, 8);
+                    d += __shfl_xor_sync(0xffffffffu, d, 16);
+                    nrm[CPT + es] = d;
+                }
+            }
         }
     }
     __syncthreads();                                     // dvec / taus / rdia / perm / colstep of the last step visible
@@ -438,26 +519,24 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
         double* Tg = L.Tphys + (long long)mat * L.strideTp;
         const int n_tot = p.n;
 #pragma unroll
-        for (int e = 0; e < CPT; ++e) {
-            const int s = (warp * CPT + e) * 4 + t;
+        for (int e = 0; e < CT; ++e) {
+            const int s = (warp * CT + e) * 4 + t;
             if (s < nloc) {
                 const int col = s * CS + rank;
                 const int pc = cmap ? cmap[col] : col;
                 const int js = colstep[s];
                 double* tc = Tg + joff + (long long)pc * p.ld;
-                if (js >= 0) {                           // pivoted at this level: rows < js are R, row js is R_jj, the rest 0
-                    const double djs = rdia[js] / dvec[js];
 #pragma unroll
-                    for (int i = 0; i < RPT; ++i) {
-                        const int row = 8 * i + g;
+                for (int i = 0; i < RPT; ++i) {
+                    const int row = 8 * i + g;
+                    double x;
+                    if (e < CPT) x = a[e < CPT ? e : 0][i];
+                    else { const double2 xx = STRIP(e - CPT, i >> 1); x = (i & 1) ? xx.y : xx.x; }
+                    if (js >= 0) {                       // pivoted at this level: rows < js are R, row js is R_jj, the rest 0
                         if (joff + row < n_tot)
-                            tc[row] = (row < js) ? a[e][i] / dvec[row] : ((row == js) ? djs : 0.0);
-                    }
-                } else {                                 // still active: rows < jstop are final (R12)
-#pragma unroll
-                    for (int i = 0; i < RPT; ++i) {
-                        const int row = 8 * i + g;
-                        if (row < jstop) tc[row] = a[e][i] / dvec[row];
+                            tc[row] = (row < js) ? x / dvec[row] : ((row == js) ? rdia[js] / dvec[js] : 0.0);
+                    } else {                             // still active: rows < jstop are final (R12)
+                        if (row < jstop) tc[row] = x / dvec[row];
                     }
                 }
             }
@@ -468,8 +547,8 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
         double* Sg = L.S + (long long)mat * L.strideS;
         int* cmo = L.cmap_out + (long long)mat * L.strideCmapOut;
 #pragma unroll
-        for (int e = 0; e < CPT; ++e) {
-            const int s = (warp * CPT + e) * 4 + t;
+        for (int e = 0; e < CT; ++e) {
+            const int s = (warp * CT + e) * 4 + t;
             const bool live = s < nloc && colstep[s] < 0;
             const int col = s * CS + rank;
             // compact index = number of still-active columns with a smaller index
@@ -487,35 +566,43 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
 #pragma unroll
                 for (int i = 0; i < RPT; ++i) {
                     const int row = 8 * i + g;
-                    if (row >= jstop && row < n) Sg[(row - jstop) + (long long)k * L.ldS] = a[e][i];
+                    double x;
+                    if (e < CPT) x = a[e < CPT ? e : 0][i];
+                    else { const double2 xx = STRIP(e - CPT, i >> 1); x = (i & 1) ? xx.y : xx.x; }
+                    if (row >= jstop && row < n) Sg[(row - jstop) + (long long)k * L.ldS] = x;
                 }
             }
         }
     }
 }
+#undef STRIP
 
 // ================================================================================================
 // host side: geometry table and launch
 // ================================================================================================
+// (rows per thread, register columns per thread, strip columns per thread)
 #define UDT_FOR_EACH_GEOM(X) \
-    X(2, 1) X(2, 2) X(4, 1) X(4, 2) X(8, 1) X(8, 2) X(12, 1) X(12, 2) X(12, 4) X(16, 1) X(16, 2) X(16, 4) \
-    X(20, 1) X(20, 2) X(20, 4) X(24, 1) X(24, 2) X(28, 1) X(28, 2) X(32, 1) X(32, 2) X(36, 1) X(36, 2)
+    X(2, 1, 0) X(2, 2, 0) X(4, 1, 0) X(4, 2, 0) X(8, 1, 0) X(8, 2, 0) X(12, 1, 0) X(12, 2, 0) X(12, 4, 0) X(16, 1, 0) X(16, 2, 0) \
+    X(16, 4, 0) X(20, 1, 0) X(20, 2, 0) X(20, 4, 0) X(24, 1, 0) X(24, 2, 0) X(28, 1, 0) X(28, 2, 0) X(32, 1, 0) X(32, 2, 0) \
+    X(36, 1, 0) X(36, 2, 0) X(32, 1, 1)
 
-struct UdtKernelEntry { int rpt, cpt, max_threads; const void* fn; };
+struct UdtKernelEntry { int rpt, cpt, cps, max_threads; const void* fn; };
 static const UdtKernelEntry* udt_kernel_table(int& count)
 {
-#define UDT_ENTRY(R, C) {R, C, udt_max_threads(R, C), (const void*)udt_steps_kernel<R, C>},
+#define UDT_ENTRY(R, C, S) {R, C, S, udt_max_threads(R, C), (const void*)udt_steps_kernel<R, C, S>},
     static const UdtKernelEntry table[] = {UDT_FOR_EACH_GEOM(UDT_ENTRY)};
 #undef UDT_ENTRY
     count = (int)(sizeof(table) / sizeof(table[0]));
     return table;
 }
 
-static size_t udt_steps_smem(int rpt, int cpt, int cs, int nwarps, int n)
+static size_t udt_steps_smem(int rpt, int cpt, int cps, int cs, int nwarps, int n)
 {
     const int vb = 8 * (rpt + 2), ve = vb + 4;
-    return ((size_t)2 * cs * ve + 2 * ve + vb + 3 * (size_t)n + 32 + 2) * sizeof(double) +
-           ((size_t)nwarps * 4 * cpt + n + 32) * sizeof(int);
+    size_t b = ((size_t)2 * cs * ve + 2 * ve + vb + 3 * (size_t)n + 32 + 2) * sizeof(double) +
+               ((size_t)nwarps * 4 * (cpt + cps) + n + 32) * sizeof(int);
+    if (cps > 0) b += 16 + (size_t)cps * (rpt / 2) * nwarps * 32 * 16;   // strips (16-byte aligned)
+    return b;
 }
 
 // Chooses the geometry that keeps the most matrices in flight per SM (registers: what the launch bound of the
@@ -533,14 +620,14 @@ bool udt_steps_geometry(int nk, UdtLevel& g)
     double best_score = -1.0;
     for (int k = 0; k < count; ++k) {
         if (tab[k].rpt != rpt) continue;
-        const int cpt = tab[k].cpt, maxw = tab[k].max_threads / 32;
+        const int cpt = tab[k].cpt, cps = tab[k].cps, maxw = tab[k].max_threads / 32;
         const int regs = (tab[k].max_threads == 512) ? 128 : ((tab[k].max_threads == 384) ? 168 : 255);
         for (int cs = 1; cs <= 8; ++cs) {
             const int nloc = (nk + cs - 1) / cs;
-            const int w = (nloc + 4 * cpt - 1) / (4 * cpt);
+            const int w = (nloc + 4 * (cpt + cps) - 1) / (4 * (cpt + cps));
             if (w > maxw || w > 16) continue;
             const int threads = w * 32;
-            const size_t smem = udt_steps_smem(rpt, cpt, cs, w, nk);
+            const size_t smem = udt_steps_smem(rpt, cpt, cps, cs, w, nk);
             int per_sm = 65536 / (regs * threads);
             per_sm = std::min(per_sm, 2048 / threads);
             per_sm = std::min(per_sm, (int)((227 * 1024) / (smem + 1024)));
@@ -548,10 +635,14 @@ bool udt_steps_geometry(int nk, UdtLevel& g)
             if (per_sm < 1) continue;
             // (measured at n = 256: 16 warps x 1 column per thread 1.51 ms, 8 warps x 2 columns 1.57 ms -- latency bound;
             //  preferring FEWER warps at every level: 256 -> 1.58 vs 1.62, 128 -> 0.180 vs 0.172, n = 144 0.80 vs 0.74 ms per call)
-            const double score = (double)per_sm / cs + 1e-3 * w;
+            // A hybrid step pays three shared-memory passes over the strips.  Measured on 296 x 256^2: 5.8 us per step on
+            // clusters of 2 (74 matrices in flight) against 2.6 us on clusters of 4 (33): 1.48 vs 1.63 ms for the 256-column
+            // level; the 192-column level on ONE hybrid CTA per matrix: 6.0 us per step, 0.77 vs 0.68 ms -- slower; n = 288
+            // on hybrid clusters of 3 instead of 5: no change.  The factor below keeps exactly the first case.
+            const double score = (double)per_sm / cs / (cps > 0 ? 1.9 : 1.0) + 1e-3 * w;
             if (score > best_score) {
                 best_score = score;
-                g.cs = cs; g.cpt = cpt; g.rpt = rpt; g.nwarps = w; g.smem = smem;
+                g.cs = cs; g.cpt = cpt; g.cps = cps; g.rpt = rpt; g.nwarps = w; g.smem = smem;
             }
             break;                                       // larger clusters only lose from here
         }
@@ -565,7 +656,7 @@ cudaError_t launch_udt_steps(const UdtParams& p, const UdtLevel& L, cudaStream_t
     const UdtKernelEntry* tab = udt_kernel_table(count);
     const void* fn = nullptr;
     for (int k = 0; k < count; ++k)
-        if (tab[k].rpt == L.rpt && tab[k].cpt == L.cpt) fn = tab[k].fn;
+        if (tab[k].rpt == L.rpt && tab[k].cpt == L.cpt && tab[k].cps == L.cps) fn = tab[k].fn;
     if (!fn) return cudaErrorInvalidConfiguration;
     if (L.smem > 48 * 1024) {
         static SmemAttr attr[64];                        // one per table entry
