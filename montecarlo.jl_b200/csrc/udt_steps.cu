@@ -368,13 +368,14 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
             }
         }
         // ---- apply H_j to the active columns, fused recomputation of the remaining norms -------------------
+        // (register columns e < CPT and strip columns e >= CPT in the same passes: one read of v, one butterfly phase)
         if (__any_sync(0xffffffffu, act != 0u)) {        // warp-uniform: the butterflies below need all 32 lanes
             constexpr int GS = (RPT % 8 == 0) ? 8 : ((RPT % 4 == 0) ? 4 : 2);   // rows-of-8 per group: one skip test per group
             const int gi0 = (j >> 3) / GS;               // groups below hold only finished rows (v = 0 there)
             const double* vb = vw + g * VP;
-            double d0[CPT], d1[CPT];
+            double d0[CT], d1[CT];
 #pragma unroll
-            for (int e = 0; e < CPT; ++e) d0[e] = d1[e] = 0.0;
+            for (int e = 0; e < CT; ++e) d0[e] = d1[e] = 0.0;
 #pragma unroll
             for (int gi = 0; gi < RPT / GS; ++gi)
                 if (gi >= gi0) {                         // uniform over the CTA
@@ -382,12 +383,17 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
                     for (int i = gi * GS; i < gi * GS + GS; i += 2) {
                         const double2 v = *reinterpret_cast<const double2*>(vb + i);
 #pragma unroll
-                        for (int e = 0; e < CPT; ++e) { d0[e] = fma(v.x, a[e][i], d0[e]); d1[e] = fma(v.y, a[e][i + 1], d1[e]); }
+                        for (int e = 0; e < CT; ++e) {
+                            double2 x;
+                            if (e < CPT) x = make_double2(a[e < CPT ? e : 0][i], a[e < CPT ? e : 0][i + 1]);
+                            else x = STRIP(e - CPT, i >> 1);
+                            d0[e] = fma(v.x, x.x, d0[e]); d1[e] = fma(v.y, x.y, d1[e]);
+                        }
                     }
                 }
-            double sd[CPT];
+            double sd[CT];
 #pragma unroll
-            for (int e = 0; e < CPT; ++e) {
+            for (int e = 0; e < CT; ++e) {
                 double d = d0[e] + d1[e];
                 d += __shfl_xor_sync(0xffffffffu, d, 4);
                 d += __shfl_xor_sync(0xffffffffu, d, 8);
@@ -395,7 +401,7 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
                 sd[e] = ((act >> e) & 1u) ? -tau * d : 0.0;
             }
 #pragma unroll
-            for (int e = 0; e < CPT; ++e) d0[e] = d1[e] = 0.0;      // now the norm accumulators
+            for (int e = 0; e < CT; ++e) d0[e] = d1[e] = 0.0;      // now the norm accumulators
 #pragma unroll
             for (int gi = 0; gi < RPT / GS; ++gi) {
                 if (gi > gi0) {
@@ -403,9 +409,16 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
                     for (int i = gi * GS; i < gi * GS + GS; i += 2) {
                         const double2 v = *reinterpret_cast<const double2*>(vb + i);
 #pragma unroll
-                        for (int e = 0; e < CPT; ++e) {
-                            const double x0 = fma(v.x, sd[e], a[e][i]), x1 = fma(v.y, sd[e], a[e][i + 1]);
-                            a[e][i] = x0; a[e][i + 1] = x1;
+                        for (int e = 0; e < CT; ++e) {
+                            double x0, x1;
+                            if (e < CPT) {
+                                x0 = fma(v.x, sd[e], a[e < CPT ? e : 0][i]); x1 = fma(v.y, sd[e], a[e < CPT ? e : 0][i + 1]);
+                                a[e < CPT ? e : 0][i] = x0; a[e < CPT ? e : 0][i + 1] = x1;
+                            } else {
+                                const double2 x = STRIP(e - CPT, i >> 1);
+                                x0 = fma(v.x, sd[e], x.x); x1 = fma(v.y, sd[e], x.y);
+                                STRIP(e - CPT, i >> 1) = make_double2(x0, x1);
+                            }
                             d0[e] = fma(x0, x0, d0[e]); d1[e] = fma(x1, x1, d1[e]);
                         }
                     }
@@ -415,9 +428,16 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
                         const double2 v = *reinterpret_cast<const double2*>(vb + i);
                         const bool k0 = 8 * i + g > j, k1 = 8 * i + 8 + g > j;
 #pragma unroll
-                        for (int e = 0; e < CPT; ++e) {
-                            const double x0 = fma(v.x, sd[e], a[e][i]), x1 = fma(v.y, sd[e], a[e][i + 1]);
-                            a[e][i] = x0; a[e][i + 1] = x1;
+                        for (int e = 0; e < CT; ++e) {
+                            double x0, x1;
+                            if (e < CPT) {
+                                x0 = fma(v.x, sd[e], a[e < CPT ? e : 0][i]); x1 = fma(v.y, sd[e], a[e < CPT ? e : 0][i + 1]);
+                                a[e < CPT ? e : 0][i] = x0; a[e < CPT ? e : 0][i + 1] = x1;
+                            } else {
+                                const double2 x = STRIP(e - CPT, i >> 1);
+                                x0 = fma(v.x, sd[e], x.x); x1 = fma(v.y, sd[e], x.y);
+                                STRIP(e - CPT, i >> 1) = make_double2(x0, x1);
+                            }
                             const double m0 = k0 ? x0 : 0.0, m1 = k1 ? x1 : 0.0;
                             d0[e] = fma(m0, m0, d0[e]); d1[e] = fma(m1, m1, d1[e]);
                         }
@@ -425,80 +445,12 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
                 }
             }
 #pragma unroll
-            for (int e = 0; e < CPT; ++e) {
+            for (int e = 0; e < CT; ++e) {
                 double d = d0[e] + d1[e];
                 d += __shfl_xor_sync(0xffffffffu, d, 4);
                 d += __shfl_xor_sync(0xffffffffu, d, 8);
                 d += __shfl_xor_sync(0xffffffffu, d, 16);
                 nrm[e] = d;
-            }
-            // ---- the same for the strip columns (shared memory; only compiled for the hybrid geometries) ---------
-            if constexpr (CPS > 0) {
-                double e0[CPS], e1[CPS];
-#pragma unroll
-                for (int es = 0; es < CPS; ++es) e0[es] = e1[es] = 0.0;
-#pragma unroll
-                for (int gi = 0; gi < RPT / GS; ++gi)
-                    if (gi >= gi0) {
-#pragma unroll
-                        for (int i = gi * GS; i < gi * GS + GS; i += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(vb + i);
-#pragma unroll
-                            for (int es = 0; es < CPS; ++es) {
-                                const double2 x = STRIP(es, i >> 1);
-                                e0[es] = fma(v.x, x.x, e0[es]); e1[es] = fma(v.y, x.y, e1[es]);
-                            }
-                        }
-                    }
-                double se[CPS];
-#pragma unroll
-                for (int es = 0; es < CPS; ++es) {
-                    double d = e0[es] + e1[es];
-                    d += __shfl_xor_sync(0xffffffffu, d, 4);
-                    d += __shfl_xor_sync(0xffffffffu, d, 8);
-                    d += __shfl_xor_sync(0xffffffffu, d, 16);
-                    se[es] = ((act >> (CPT + es)) & 1u) ? -tau * d : 0.0;
-                }
-#pragma unroll
-                for (int es = 0; es < CPS; ++es) e0[es] = e1[es] = 0.0;
-#pragma unroll
-                for (int gi = 0; gi < RPT / GS; ++gi) {
-                    if (gi > gi0) {
-#pragma unroll
-                        for (int i = gi * GS; i < gi * GS + GS; i += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(vb + i);
-#pragma unroll
-                            for (int es = 0; es < CPS; ++es) {
-                                double2 x = STRIP(es, i >> 1);
-                                x.x = fma(v.x, se[es], x.x); x.y = fma(v.y, se[es], x.y);
-                                STRIP(es, i >> 1) = x;
-                                e0[es] = fma(x.x, x.x, e0[es]); e1[es] = fma(x.y, x.y, e1[es]);
-                            }
-                        }
-                    } else if (gi == gi0) {
-#pragma unroll
-                        for (int i = gi * GS; i < gi * GS + GS; i += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(vb + i);
-                            const bool k0 = 8 * i + g > j, k1 = 8 * i + 8 + g > j;
-#pragma unroll
-                            for (int es = 0; es < CPS; ++es) {
-                                double2 x = STRIP(es, i >> 1);
-                                x.x = fma(v.x, se[es], x.x); x.y = fma(v.y, se[es], x.y);
-                                STRIP(es, i >> 1) = x;
-                                const double m0 = k0 ? x.x : 0.0, m1 = k1 ? x.y : 0.0;
-                                e0[es] = fma(m0, m0, e0[es]); e1[es] = fma(m1, m1, e1[es]);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int es = 0; es < CPS; ++es) {
-                    double d = e0[es] + e1[es];
-                    d += __shfl_xor_sync(0xffffffffu, d, 4);
-                    d += __shfl_xor_sync(0xffffffffu, d, 8);
-                    d += __shfl_xor_sync(0xffffffffu, d, 16);
-                    nrm[CPT + es] = d;
-                }
             }
         }
     }
@@ -635,10 +587,11 @@ bool udt_steps_geometry(int nk, UdtLevel& g)
             if (per_sm < 1) continue;
             // (measured at n = 256: 16 warps x 1 column per thread 1.51 ms, 8 warps x 2 columns 1.57 ms -- latency bound;
             //  preferring FEWER warps at every level: 256 -> 1.58 vs 1.62, 128 -> 0.180 vs 0.172, n = 144 0.80 vs 0.74 ms per call)
-            // A hybrid step pays three shared-memory passes over the strips.  Measured on 296 x 256^2: 5.8 us per step on
-            // clusters of 2 (74 matrices in flight) against 2.6 us on clusters of 4 (33): 1.48 vs 1.63 ms for the 256-column
-            // level; the 192-column level on ONE hybrid CTA per matrix: 6.0 us per step, 0.77 vs 0.68 ms -- slower; n = 288
-            // on hybrid clusters of 3 instead of 5: no change.  The factor below keeps exactly the first case.
+            // A hybrid step pays three shared-memory passes over the strips.  Measured on 296 x 256^2: 5.1 us per step on
+            // clusters of 2 (74 matrices in flight) against 2.6 us on clusters of 4 (33): 1.29 vs 1.63 ms for the 256-column
+            // level (1.48 while the strip columns had their own dot / update passes behind the register columns' instead
+            // of sharing them); the 192-column level on ONE hybrid CTA per matrix: 0.69 vs 0.69 ms; n = 288 on hybrid
+            // clusters of 3 instead of 5: 2.45 vs 2.39 ms per call.  The factor below keeps exactly the first case.
             const double score = (double)per_sm / cs / (cps > 0 ? 1.9 : 1.0) + 1e-3 * w;
             if (score > best_score) {
                 best_score = score;
