@@ -197,6 +197,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             const int col = n0 + wn0 + j * 8 + 2 * t + e;
             csv[j][e] = (has_cs && col < p.N) ? scale_at(p.cs, mat, col) : 1.0;
         }
+    // Interior tiles without a diagonal term or a read of C take a branch-free path: the general path below is one
+    // dependent chain of bounds checks, 64-bit index arithmetic and branches PER ELEMENT (measured with clock64: ~340
+    // cycles per element, 11 000 cycles = 20 % of the life of a 64 x 64 x 256 CTA), this one a handful of independent
+    // multiplies and stores per element.
+    const bool fast = (m0 + BM <= p.M) && (n0 + BN <= p.N) && !p.add_diag && (p.beta == 0.0 || preload);
+    if (fast) {
+        double rsv[MI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) rsv[i] = has_rs ? scale_at(p.rs, mat, m0 + wm0 + i * 8 + g) : 1.0;
+        const double alpha = p.alpha;
+        double* cb = C + (m0 + wm0 + g) + (long long)(n0 + wn0 + 2 * t) * p.ldc;
+        const long long ldc = p.ldc;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double* cc = cb + (long long)(j * 8 + e) * ldc;
+#pragma unroll
+                for (int i = 0; i < MI; ++i) {
+                    double v = alpha * acc[i][j][e] * rsv[i];        // same order of the factors as the general path
+                    if (has_cs) v *= csv[j][e];
+                    cc[i * 8] = v;
+                }
+            }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
         const int row = m0 + wm0 + i * 8 + g;
@@ -299,7 +325,12 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
     // either: 32.1 (34.0 with the 8 x longer k loop).  A 64 x 128 tile without producer warp whose slots are re-armed by
     // the LAST consumer warp to finish them (shared-memory counter, nobody waits): 26.5 as well; compiling the inner
     // diagonal factor out, constant instead of random operands: no change.  What separates the 64 x 128 kernel (two warps
-    // per scheduler, 72 % of the pipe) from the microbenchmark (99 % with two) was not found.
+    // per scheduler, 72 % of the pipe) from the microbenchmark (99 % with two) was found with clock64 stamps inside the kernel:
+    // the EPILOGUE.  Its per-element chain of bounds checks, 64-bit index arithmetic and branches took ~340 cycles per element
+    // -- 11 000 cycles (20 %) of the life of a 64 x 64 CTA, 21 000-28 000 (23-28 %) of a 64 x 128 one -- and predicating only
+    // the store (the "no epilogue" experiment above) left all of it in place.  With the branch-free path for interior tiles:
+    // 32.1 standalone (cuBLAS batched 32.95), 30.7 in the sweep; consumer-only upper bound at K = 256 (no loads, no
+    // barriers) 32.7 for both the 64 x 64 and the 64 x 128 tile, so the large tile has nothing left to give.
     if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4, 3>(p, st);
     if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
     return launch_cfg<32, 32, 16, 16, TA, TB>(p, st);
