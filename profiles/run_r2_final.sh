@@ -3,7 +3,7 @@
 # `ncu --set full` capture of each hot kernel (raw + details pages; kernels selected by name and launch index).
 set -u
 O=gpurun_out
-P=r2f
+P=r2g
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${P}_launches_cfg4shape.csv python profiles/prof_workload.py 1 > $O/${P}_prof.log 2>&1
 cap() {  # name kernel skip script args...
   local name=$1 k=$2 skip=$3; shift 3
