@@ -317,7 +317,10 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
             // one CTA per matrix: the entry is written in place and the CTA barrier below publishes it -- no copy engine,
             // no proxy fence, no mbarrier round trip on the critical path of the step
             double* sb = (CS > 1) ? sendbuf + q * VE : vbuf + (size_t)q * VE;
-            for (int idx = 2 * lane; idx < VB; idx += 64) {
+#pragma unroll
+            for (int it = 0; it < (VB + 63) / 64; ++it) {          // unrolled: the LDS -> DMUL -> STS chains of the rounds overlap
+                const int idx = 2 * lane + 64 * it;
+                if (idx >= VB) break;
                 const int gg = idx / VP, ii = idx - gg * VP;
                 double2 y = make_double2(0.0, 0.0);
                 if (live_w && ii < RPT) {
@@ -370,6 +373,7 @@ udt_steps_kernel(const UdtParams p, const UdtLevel L)
                 if (g == 0) colstep[s] = j;
             }
             double* vcol = Vg + (long long)(joff + j) * ldv;
+#pragma unroll 1                                         // (unrolled, the run-time stride costs an integer division for the trip count every step)
             for (int r = tid; r < ldv; r += nwarps * 32) {
                 const int lr = r - joff;
                 vcol[r] = (lr >= 0 && lr < 8 * RPT) ? vw[(lr & 7) * VP + (lr >> 3)] : 0.0;
