@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateParams p, const
                     Rv[b] = 1.0 + Dl[b] * (1.0 - gii);
                 }
                 const double prob = proposal_prob(p.kind, pr, (nb == 1) ? Rv[0] * Rv[0] : Rv[0] * Rv[1]);
+                __syncwarp();                                   // every lane has read sconf[i] before lane 0 may overwrite it
                 if (lane == 0) {
                     if (p.check_sign && prob < 0.0) {
                         neg_cnt += 1.0; neg_sum += log10(fabs(prob));
