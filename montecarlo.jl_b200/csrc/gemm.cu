@@ -331,7 +331,13 @@ static cudaError_t launch_tiles(const GemmParams& p, cudaStream_t st)
     // the store (the "no epilogue" experiment above) left all of it in place.  With the branch-free path for interior tiles:
     // 32.1 standalone (cuBLAS batched 32.95), 30.7 in the sweep; consumer-only upper bound at K = 256 (no loads, no
     // barriers) 32.7 for both the 64 x 64 and the 64 x 128 tile, so the large tile has nothing left to give.
-    if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4, 3>(p, st);
+    if (w64 <= w48 + 1e-9 && w64 <= w32 + 1e-9) {
+        // transposed A: BOTH operand tiles are k-major, i.e. boxes of 64 rows of BK + 4 doubles; at BK = 16 the 160-byte rows
+        // cost the TMA engine more requests per byte (0.360 against 0.325 ms per 296 x 256^3 launch for the plain variant); with
+        // BK = 32 and two stages (same shared memory, 288-byte rows) the transposed variant runs at 0.325 ms too
+        if constexpr (TA) return launch_cfg<64, 64, 32, 32, TA, TB, 32, 2, 3>(p, st);
+        else return launch_cfg<64, 64, 32, 32, TA, TB, 16, 4, 3>(p, st);
+    }
     if (w48 <= w32 + 1e-9) return launch_cfg<48, 48, 24, 24, TA, TB>(p, st);
     return launch_cfg<32, 32, 16, 16, TA, TB>(p, st);
 }
