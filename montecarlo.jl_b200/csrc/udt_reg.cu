@@ -303,6 +303,8 @@ static int udt_next_level_size(int nk)
     // (measured, 296 x 256^2: a 224-column level on clusters of 3 -- 48 in flight, 7 waves, 3.4 us per step with 10 fat
     //  warps -- 0.76 ms for its 32 steps against 0.75 ms on the clusters of 4: no gain; 96 columns fit two matrices per SM:
     //  128 -> 64 in 0.27 instead of 0.32 ms)
+    // (a 224-column HYBRID level on clusters of 2 between 256 and 192: 0.70 + 0.57 ms against 1.20 ms for the 64 steps on the
+    //  256-column level alone -- a level's load / export of the 512 KB matrix costs ~0.1 ms, more than the cheaper steps save)
     static const int sizes[5] = {256, 192, 128, 96, 64};
     for (int k = 0; k < 5; ++k)
         if (sizes[k] < nk) return sizes[k];
