@@ -25,6 +25,12 @@
 // X build grow faster than the flush shrinks: cfg 5 (one flavor, 4 x 4 patches on all 256 threads) window 40 / 48 / 56 / 64
 // = 0.624 / 0.640 / 0.640 / 0.680 ms per slice visit; cfg 4 (two flavors: 4 x 8 patches) 0.97 against 0.83 ms.  Smaller
 // blocks lose as well (cfg 4: 36 -> 0.850, 32 -> 0.850, 24 -> 1.04): the kb the host picks is the optimum.
+// Measured in the last session of round 2 and not kept: (a) taking the column / row of an accepted site from the register patches
+// with one uniform switch on j & 3 instead of the selects (what gave slice_steps_kernel +7 % at cfg 2): cfg 4 252.8 -> 253.6 ms
+// of update per sweep, cfg 5 124.9 -> 126.1; (b) on top of it, compile-time thread count and division-free index arithmetic in
+// the X build (the run-time `e / (k * k)`, `r % k` cost ~25 instructions each): cfg 4 250.9, cfg 3 49.6 -> 49.3, but cfg 5
+// 128.4-128.9 -- ptxas' spill pattern of this 255-register kernel moves with every change (NB = 2: 96 -> 168 bytes of stack,
+// NB = 1: 120 -> 48) and decides more than the instructions saved.
 // Also without effect: walking the tiles of the flush in reverse order on every other block, so that a flush starts with the
 // tiles the previous flush of the same flavor wrote last (L2 reuse: 155 MB of G against 126 MB of L2): 0.800 vs 0.799 ms.
 #include "common.cuh"
@@ -255,32 +261,14 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
             double* cvb = colv + (a & 1) * nb * kb;
             double* rvb = rowv + (a & 1) * nb * kb;
             if (owner) {
-                // column j & 3 / row j & 3 of the 4 x 4 patch: the patches are aligned to multiples of 4, so the index inside
-                // the patch is uniform over the CTA -- one uniform switch instead of 32 selects on the register patch
-                double pc[4], prw[4];
-                switch (j & 3) {
-                case 0:
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { pc[q] = g[q][0]; prw[q] = g[0][q]; }
-                    break;
-                case 1:
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { pc[q] = g[q][1]; prw[q] = g[1][q]; }
-                    break;
-                case 2:
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { pc[q] = g[q][2]; prw[q] = g[2][q]; }
-                    break;
-                default:
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { pc[q] = g[q][3]; prw[q] = g[3][q]; }
-                    break;
-                }
                 if (j >= oyb && j < oyb + 4) {              // this patch holds part of column j
 #pragma unroll
                     for (int ix = 0; ix < 4; ++ix) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int iy = 0; iy < 4; ++iy) v = (oyb + iy == j) ? g[ix][iy] : v;
                         const int x = oxb + ix;
-                        const double cv = pc[ix] - ((x == j) ? 1.0 : 0.0);
+                        const double cv = v - ((x == j) ? 1.0 : 0.0);
                         cvb[ob * kb + x] = cv;
                         Ub[((size_t)ob * kb + x) * RP + a] = cv;
                     }
@@ -289,8 +277,11 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
                     const double cc = ob ? c1 : c0;
 #pragma unroll
                     for (int iy = 0; iy < 4; ++iy) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int ix = 0; ix < 4; ++ix) v = (oxb + ix == j) ? g[ix][iy] : v;
                         const int y = oyb + iy;
-                        const double rv = cc * prw[iy];
+                        const double rv = cc * v;
                         rvb[ob * kb + y] = rv;
                         Wb[((size_t)ob * kb + a) * RP + y] = rv;
                     }
