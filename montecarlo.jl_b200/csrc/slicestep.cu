@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256)
 slice_steps_kernel(const SliceStepParams p)
 {
     extern __shared__ __align__(16) double sm[];
-    const int n = p.n, ldg = p.ldg, tid = threadIdx.x, NT = blockDim.x;
+    constexpr int NT = 256;                                  // the launches below (compile-time strides: no trip-count divisions)
+    const int n = p.n, ldg = p.ldg, tid = threadIdx.x;
     const int chain = blockIdx.x;
     double* Gs = sm;                                     // [NB][n][ldg]
     double* Ts = Gs + (size_t)NB * n * ldg;              // [n][ldg] wrap intermediate (one flavor at a time)
@@ -388,7 +389,8 @@ __global__ void __launch_bounds__(256)
 slice_chain_kernel(const SliceChainParams p)
 {
     extern __shared__ __align__(16) double sm[];
-    const int n = p.n, ldg = p.ldg, tid = threadIdx.x, NT = blockDim.x;
+    constexpr int NT = 256;                                  // the launches below (compile-time strides: no trip-count divisions)
+    const int n = p.n, ldg = p.ldg, tid = threadIdx.x;
     const int mat = blockIdx.x, chain = mat / p.nb, blk = mat - chain * p.nb;
     double* Ma = sm;                                     // [n][ldg]
     double* Mb = Ma + (size_t)n * ldg;                   // [n][ldg]
