@@ -177,20 +177,23 @@ slice_steps_kernel(const SliceStepParams p)
         }
         int k = 0, next = 0;
         for (;;) {
-            double prob[2], cf[2];
-            int acc[2];
+            // the half of the sites that holds `next` first; the other half only if nothing was accepted there (uniform
+            // branches: the evaluation of a half is ~45 of the ~270 instructions of an accept)
+            double prob[2] = {0.0, 0.0}, cf[2] = {0.0, 0.0};
+            unsigned b0 = 0u, b1 = 0u;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int j = lane + 32 * h;
-                const bool elig = (j >= next) && (j < n);
-                const double Rv = 1.0 + pr[h].Dl[0] * (1.0 - gd[h]);
-                cf[h] = pr[h].Dl[0] * ss_rcp(Rv);                    // Delta / R, speculative
-                prob[h] = proposal_prob(p.kind, pr[h], Rv * Rv);
-                const int a_ = (fc[h] >= 0) ? (fc[h] != 0) : ((prob[h] > 1.0) || (un[h] < prob[h]));
-                acc[h] = elig ? a_ : 0;
+                if ((h == 0) ? (next < 32) : (b0 == 0u)) {
+                    const int j = lane + 32 * h;
+                    const bool elig = (j >= next) && (j < n);
+                    const double Rv = 1.0 + pr[h].Dl[0] * (1.0 - gd[h]);
+                    cf[h] = pr[h].Dl[0] * ss_rcp(Rv);                    // Delta / R, speculative
+                    prob[h] = proposal_prob(p.kind, pr[h], Rv * Rv);
+                    const int a_ = (fc[h] >= 0) ? (fc[h] != 0) : ((prob[h] > 1.0) || (un[h] < prob[h]));
+                    const unsigned bb = __ballot_sync(0xffffffffu, elig ? a_ : 0);
+                    if (h == 0) b0 = bb; else b1 = bb;
+                }
             }
-            const unsigned b0 = __ballot_sync(0xffffffffu, acc[0]);
-            const unsigned b1 = __ballot_sync(0xffffffffu, acc[1]);
             const int jacc = b0 ? (__ffs(b0) - 1) : (b1 ? 32 + __ffs(b1) - 1 : -1);
             if (warp == 0) {                                 // traces and statistics of the real decisions
                 const int jlast = (jacc >= 0) ? jacc : n - 1;
