@@ -31,6 +31,10 @@
 // the X build (the run-time `e / (k * k)`, `r % k` cost ~25 instructions each): cfg 4 250.9, cfg 3 49.6 -> 49.3, but cfg 5
 // 128.4-128.9 -- ptxas' spill pattern of this 255-register kernel moves with every change (NB = 2: 96 -> 168 bytes of stack,
 // NB = 1: 120 -> 48) and decides more than the instructions saved.
+// (c) evaluating only the half of the sites that holds the next proposal (what slice_steps_kernel does now): cfg 4 252.0, cfg 5
+// 125.3, cfg 3 49.3 -- within noise of the kept kernel.  With two warps per scheduler the serial phase follows the dependent chain
+// of an accept (decision -> ballot -> shuffle -> extraction -> barrier -> rank-1 update of the diagonal), not the length of the
+// instruction stream around it.
 // Also without effect: walking the tiles of the flush in reverse order on every other block, so that a flush starts with the
 // tiles the previous flush of the same flavor wrote last (L2 reuse: 155 MB of G against 126 MB of L2): 0.800 vs 0.799 ms.
 #include "common.cuh"
