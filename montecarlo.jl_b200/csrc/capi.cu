@@ -27,11 +27,14 @@ static thread_local std::string g_create_error;
 // ---- host <-> device matrix copies (host ld = N, device ld = c->ld) ------------------------
 cudaError_t h2d_mats(dqmc_ctx* c, double* dst, const double* src, long long nmats)
 {
+    // equal pitches: ONE contiguous copy (a 2-D copy is issued row by row: 2 KB pieces at n = 256)
+    if (c->ld == c->N) return cudaMemcpyAsync(dst, src, (size_t)c->N * c->N * nmats * 8, cudaMemcpyHostToDevice, c->st);
     return cudaMemcpy2DAsync(dst, (size_t)c->ld * 8, src, (size_t)c->N * 8, (size_t)c->N * 8,
                              (size_t)c->N * nmats, cudaMemcpyHostToDevice, c->st);
 }
 cudaError_t d2h_mats(dqmc_ctx* c, double* dst, const double* src, long long nmats)
 {
+    if (c->ld == c->N) return cudaMemcpyAsync(dst, src, (size_t)c->N * c->N * nmats * 8, cudaMemcpyDeviceToHost, c->st);
     return cudaMemcpy2DAsync(dst, (size_t)c->N * 8, src, (size_t)c->ld * 8, (size_t)c->N * 8,
                              (size_t)c->N * nmats, cudaMemcpyDeviceToHost, c->st);
 }
