@@ -368,6 +368,10 @@ def main():
     c_host = torch.empty((B, M, N), dtype=torch.int8).pin_memory()
     rng_t = torch.Generator().manual_seed(SEED + 17 * rank)
     u_host.uniform_(generator=rng_t)     # the host's own RNG stream (drop-in mode: Julia supplies the uniforms)
+    for _ in range(min(W, 2)):           # untimed: the table-RNG mode has its own captured graph (first sweep eager, second captures)
+        ctx.sweep(1, uniforms=u_host.numpy())
+        ctx.greens(out=g_host.numpy())
+        ctx.get_conf(out=c_host.numpy())
     barrier()
     e2e0, e2e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e0.record(stream)
