@@ -251,6 +251,15 @@ def main():
                          "CombinedGreensIterator) and the oracle's CPU time for the same; default for cfg5")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line, the JSON record: everything a library prints on fd 1 on the way (NCCL announces its
+    # version there when torch.distributed or the library's own communicator comes up) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -272,7 +281,7 @@ def main():
                                            "reference's loops (oracle/dqmc_ref.c) -- Julia is not in the image"},
                 "e2e": {"value": r["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "acceptance": r["acceptance"], "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     import torch
@@ -304,18 +313,10 @@ def main():
     if world > 1:
         # the path's only collective (final observable reduction) goes through the library's own NCCL communicator
         # on the context's stream; torch.distributed only ships the 128-byte id and does the timing barriers
-        # (NCCL announces its version on stdout when a communicator is created: keep stdout for the JSON line)
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            ids = [pkg.Context.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            ctx.comm_init(world, rank, ids[0])
-            ctx.reduce_observables()         # first collective of a communicator sets up its connections: not timed
-        finally:
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
+        ids = [pkg.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(world, rank, ids[0])
+        ctx.reduce_observables()             # first collective of a communicator sets up its connections: not timed
 
     def barrier():
         if world > 1:
@@ -515,7 +516,7 @@ def main():
                                               f"each of the same workload, {r['seconds']:.1f} s; oracle/dqmc_ref.c "
                                               "(C port, Julia absent)"}
             line["parity"] = parity_leg(pkg, args.config, dev)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.barrier()
