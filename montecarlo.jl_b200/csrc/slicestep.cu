@@ -100,8 +100,10 @@ slice_steps_kernel(const SliceStepParams p)
     const int chain = blockIdx.x;
     double* Gs = sm;                                     // [NB][n][ldg]
     double* Ts = Gs + (size_t)NB * n * ldg;              // [n][ldg] wrap intermediate (one flavor at a time)
-    double* IG = Ts + (size_t)n * ldg;                   // [2][n]  e_i - G[:, i]      (one flavor: double buffered by the
-    double* gr = IG + 2 * n;                             // [2][n]  (Delta / R) G[i, :] parity of the accept; two: per flavor)
+    double* xch = Ts + (size_t)n * ldg;                  // [2][2][64] one flavor: column / row of an accept, padded to whole patches,
+                                                         //            double buffered by the parity of the accept (128-bit accesses)
+    double* IG = xch + 256;                              // [2][n]  e_i - G[:, i]      (two flavors: per flavor)
+    double* gr = IG + 2 * n;                             // [2][n]  (Delta / R) G[i, :]
     double* dpos = gr + 2 * n;                           // [NB][n]  e^{+V} of the wrap slice
     double* dneg = dpos + NB * n;                        // [NB][n]  e^{-V}
     double* su = dneg + NB * n;                          // [n] Metropolis uniforms of the step
@@ -215,8 +217,8 @@ slice_steps_kernel(const SliceStepParams p)
             const double c0 = __shfl_sync(0xffffffffu, hh ? cf[1] : cf[0], src);
             const int j = jacc;
             if (tid == src) { sconf[j] = sxnew[j]; cl[j] = sxnew[j]; }
-            double* cvb = IG + (k & 1) * n;                  // G[:, j] - e_j   (the reference's -(e_j - G[:, j]))
-            double* rvb = gr + (k & 1) * n;                  // (Delta / R) G[j, :]
+            double* cvb = xch + (k & 1) * 64;                // G[:, j] - e_j   (the reference's -(e_j - G[:, j]))
+            double* rvb = xch + 128 + (k & 1) * 64;          // (Delta / R) G[j, :]
             if (owner) {
                 // column j & 3 / row j & 3 of the 4 x 4 patch (patches are aligned to multiples of 4: the index inside the patch
                 // is uniform over the CTA -- one uniform switch instead of 32 selects on the register patch)
@@ -239,28 +241,23 @@ slice_steps_kernel(const SliceStepParams p)
                     for (int q = 0; q < 4; ++q) { pc[q] = g[q][3]; prw[q] = g[3][q]; }
                     break;
                 }
+                // (entries >= n of a patch are zero and stay zero: whole patches are exchanged, no bounds tests)
                 if (j >= oyb && j < oyb + 4) {               // this patch holds part of column j
 #pragma unroll
-                    for (int ix = 0; ix < 4; ++ix) {
-                        const int x = oxb + ix;
-                        if (x < n) cvb[x] = pc[ix] - ((x == j) ? 1.0 : 0.0);
-                    }
+                    for (int ix = 0; ix < 4; ++ix) pc[ix] -= (oxb + ix == j) ? 1.0 : 0.0;
+                    *reinterpret_cast<double2*>(cvb + oxb) = make_double2(pc[0], pc[1]);
+                    *reinterpret_cast<double2*>(cvb + oxb + 2) = make_double2(pc[2], pc[3]);
                 }
                 if (j >= oxb && j < oxb + 4) {               // ... part of row j
-#pragma unroll
-                    for (int iy = 0; iy < 4; ++iy) {
-                        const int y = oyb + iy;
-                        if (y < n) rvb[y] = c0 * prw[iy];
-                    }
+                    *reinterpret_cast<double2*>(rvb + oyb) = make_double2(c0 * prw[0], c0 * prw[1]);
+                    *reinterpret_cast<double2*>(rvb + oyb + 2) = make_double2(c0 * prw[2], c0 * prw[3]);
                 }
             }
             __syncthreads();
             if (owner) {
-                double cv[4], rv[4];
-#pragma unroll
-                for (int ix = 0; ix < 4; ++ix) cv[ix] = (oxb + ix < n) ? cvb[oxb + ix] : 0.0;
-#pragma unroll
-                for (int iy = 0; iy < 4; ++iy) rv[iy] = (oyb + iy < n) ? rvb[oyb + iy] : 0.0;
+                const double2 c01 = *reinterpret_cast<const double2*>(cvb + oxb), c23 = *reinterpret_cast<const double2*>(cvb + oxb + 2);
+                const double2 r01 = *reinterpret_cast<const double2*>(rvb + oyb), r23 = *reinterpret_cast<const double2*>(rvb + oyb + 2);
+                const double cv[4] = {c01.x, c01.y, c23.x, c23.y}, rv[4] = {r01.x, r01.y, r23.x, r23.y};
 #pragma unroll
                 for (int iy = 0; iy < 4; ++iy)
 #pragma unroll
@@ -444,7 +441,7 @@ cudaError_t launch_slice_chain(SliceChainParams p, cudaStream_t st)
 static size_t slice_steps_smem(int n, int nb)
 {
     const int ldg = ss_ld(n);
-    return ((size_t)(nb + 1) * n * ldg + (size_t)(4 + 2 * nb) * n + n) * sizeof(double) + 2 * (size_t)n + 16;
+    return ((size_t)(nb + 1) * n * ldg + 256 + (size_t)(4 + 2 * nb) * n + n) * sizeof(double) + 2 * (size_t)n + 16;
 }
 
 bool slice_steps_supported(int n, int nb) { return n <= 64 && slice_steps_smem(n, nb) <= 110 * 1024; }
