@@ -35,6 +35,8 @@
 // 125.3, cfg 3 49.3 -- within noise of the kept kernel.  With two warps per scheduler the serial phase follows the dependent chain
 // of an accept (decision -> ballot -> shuffle -> extraction -> barrier -> rank-1 update of the diagonal), not the length of the
 // instruction stream around it.
+// (d) 128-bit loads of the exchanged column / row after the barrier (the 64-bit loads of the column are 4-way bank conflicted;
+// +4.5 % at cfg 2 in slice_steps_kernel): cfg 4 252.5, cfg 5 125.5, cfg 3 49.3 -- no change.
 // Also without effect: walking the tiles of the flush in reverse order on every other block, so that a flush starts with the
 // tiles the previous flush of the same flavor wrote last (L2 reuse: 155 MB of G against 126 MB of L2): 0.800 vs 0.799 ms.
 #include "common.cuh"
