@@ -345,19 +345,33 @@ update3_kernel(const UpdateParams p, const int ldu, const double em2a, const dou
         // X_acc[b][a1][a2] = sum_a MU[a1][a] MWt[a2][a] (compact: accepted flips only), zero padded
         for (int e = tid; e < nb * kb * RP; e += NT) XR[e] = 0.0;
         __syncthreads();
-        for (int e = tid; e < nb * k * k; e += NT) {
-            const int b = e / (k * k), r = e - b * k * k;
-            const int a2 = r % k, a1 = r / k;
-            const double* mu = Ub + ((size_t)b * kb + a1) * RP;
-            const double* mw = Wb + ((size_t)b * kb + a2) * RP;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // MU[a1][a] = 0 for a < a1, MWt[a2][a] = 0 for a < a2
-            int a = (a1 > a2 ? a1 : a2);
-            for (; a + 3 < k; a += 4) {
-                s0 = fma(mu[a], mw[a], s0); s1 = fma(mu[a + 1], mw[a + 1], s1);
-                s2 = fma(mu[a + 2], mw[a + 2], s2); s3 = fma(mu[a + 3], mw[a + 3], s3);
-            }
-            for (; a < k; ++a) s0 = fma(mu[a], mw[a], s0);
-            XR[((size_t)b * kb + a1) * RP + a2] = (s0 + s1) + (s2 + s3);
+        {
+            // on the tensor pipe: 8 x 8 tiles of X = MU MWt^T, one tile per warp at a time (as one scalar dot product per thread
+            // with two run-time divisions for its indices this loop took 10 % of the kernel's samples).  MU[a1][a] = 0 for
+            // a < a1 and MWt[a2][a] = 0 for a < a2, so the k loop of tile (ti, tj) starts at 8 max(ti, tj); rows >= k of the
+            // work matrices hold stale data that only reaches entries which are not stored.
+            const int nt = (k + 7) >> 3, k4x = (k + 3) >> 2;
+            const float inv_nt = 1.0f / (float)nt;
+            const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+            for (int b = 0; b < nb; ++b)
+                for (int tl = warp; tl < nt * nt; tl += nwarps) {
+                    const int ti = (int)(((float)tl + 0.5f) * inv_nt), tj = tl - ti * nt;
+                    const double* mu = Ub + ((size_t)b * kb + 8 * ti + gq) * RP + tq;
+                    const double* mw = Wb + ((size_t)b * kb + 8 * tj + gq) * RP + tq;
+                    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;        // two accumulator pairs: half the dependent chain
+                    int s4 = 2 * (ti > tj ? ti : tj);
+                    for (; s4 + 1 < k4x; s4 += 2) {
+                        dmma884v(c0, c1, mu[4 * s4], mw[4 * s4]);
+                        dmma884v(d0, d1, mu[4 * s4 + 4], mw[4 * s4 + 4]);
+                    }
+                    if (s4 < k4x) dmma884v(c0, c1, mu[4 * s4], mw[4 * s4]);
+                    const int a1 = 8 * ti + gq, a2 = 8 * tj + 2 * tq;
+                    if (a1 < k) {
+                        if (a2 < k) XR[((size_t)b * kb + a1) * RP + a2] = c0 + d0;
+                        if (a2 + 1 < k) XR[((size_t)b * kb + a1) * RP + a2 + 1] = c1 + d1;
+                    }
+                }
         }
         __syncthreads();
 
