@@ -177,8 +177,30 @@ slice_steps_kernel(const SliceStepParams p)
             fc[h] = (in && p.forced) ? (int)p.forced[toff + j] : -1;
             gd[h] = in ? Gs[(size_t)j * ldg + j] : 0.0;
         }
+        // The rank-1 update of an accept is applied at the TOP of the next iteration, in the same basic block as the next
+        // evaluation: its shared-memory loads and 16 FMAs overlap the evaluation's dependent chain (reciprocal, decision,
+        // ballot) instead of sitting alone behind the barrier.  Iteration 0 applies zeros.
+        for (int e = tid; e < 256; e += NT) xch[e] = 0.0;
+        __syncthreads();
+        const int lox = owner ? oxb : 0, loy = owner ? oyb : 0;   // (non-owners update a patch nobody stores)
         int k = 0, next = 0;
         for (;;) {
+            {
+                const double* pcv = xch + ((k + 1) & 1) * 64;
+                const double* prv = xch + 128 + ((k + 1) & 1) * 64;
+                const double2 c01 = *reinterpret_cast<const double2*>(pcv + lox), c23 = *reinterpret_cast<const double2*>(pcv + lox + 2);
+                const double2 r01 = *reinterpret_cast<const double2*>(prv + loy), r23 = *reinterpret_cast<const double2*>(prv + loy + 2);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int jj = lane + 32 * h;
+                    if (jj < n) gd[h] = fma(pcv[jj], prv[jj], gd[h]);
+                }
+                const double cv[4] = {c01.x, c01.y, c23.x, c23.y}, rv[4] = {r01.x, r01.y, r23.x, r23.y};
+#pragma unroll
+                for (int iy = 0; iy < 4; ++iy)
+#pragma unroll
+                    for (int ix = 0; ix < 4; ++ix) g[ix][iy] = fma(cv[ix], rv[iy], g[ix][iy]);
+            }
             // the half of the sites that holds `next` first; the other half only if nothing was accepted there (uniform
             // branches: the evaluation of a half is ~45 of the ~270 instructions of an accept)
             double prob[2] = {0.0, 0.0}, cf[2] = {0.0, 0.0};
@@ -254,20 +276,6 @@ slice_steps_kernel(const SliceStepParams p)
                 }
             }
             __syncthreads();
-            if (owner) {
-                const double2 c01 = *reinterpret_cast<const double2*>(cvb + oxb), c23 = *reinterpret_cast<const double2*>(cvb + oxb + 2);
-                const double2 r01 = *reinterpret_cast<const double2*>(rvb + oyb), r23 = *reinterpret_cast<const double2*>(rvb + oyb + 2);
-                const double cv[4] = {c01.x, c01.y, c23.x, c23.y}, rv[4] = {r01.x, r01.y, r23.x, r23.y};
-#pragma unroll
-                for (int iy = 0; iy < 4; ++iy)
-#pragma unroll
-                    for (int ix = 0; ix < 4; ++ix) g[ix][iy] = fma(cv[ix], rv[iy], g[ix][iy]);
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int jj = lane + 32 * h;
-                if (jj < n) gd[h] = fma(cvb[jj], rvb[jj], gd[h]);
-            }
             ++k; next = j + 1;
         }
         accepted += k;
