@@ -37,6 +37,8 @@
 // instruction stream around it.
 // (d) 128-bit loads of the exchanged column / row after the barrier (the 64-bit loads of the column are 4-way bank conflicted;
 // +4.5 % at cfg 2 in slice_steps_kernel): cfg 4 252.5, cfg 5 125.5, cfg 3 49.3 -- no change.
+// (e) explicitly double-buffered fragments in the T = X Br loop (7 % of the samples, DMMA issue separated by NOPs): cfg 4 245.4 ->
+// 249.0, cfg 3 47.7 -> 48.9, cfg 5 122.5 -> 120.8 (stack frame 96 -> 176 bytes at NB = 2): dropped for the headline configuration.
 // Also without effect: walking the tiles of the flush in reverse order on every other block, so that a flush starts with the
 // tiles the previous flush of the same flavor wrote last (L2 reuse: 155 MB of G against 126 MB of L2): 0.800 vs 0.799 ms.
 #include "common.cuh"
