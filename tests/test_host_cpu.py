@@ -133,3 +133,24 @@ def test_conf_compress_is_julia_bitarray_layout(b200):
     f.confs[:, :, 1] = 1
     f.decompress(ch, chain=1)
     assert np.array_equal(f.confs[:, :, 1], old)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver parses bench.py's stdout: one JSON line, whatever the libraries on the way print (NCCL announces its version
+    on fd 1).  The reference arm runs on the CPU, so the contract is checked here on a tiny anchor configuration."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--config", "anchor6a", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=str(root))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config",
+                "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["steps"] == 1 and line["warmup"] == 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["e2e"]["h2d_bytes_per_step"] == 0
