@@ -12,6 +12,12 @@
 //   * wrap: two n^3 products on the FP64 tensor pipe (DMMA m8n8k4) straight from shared memory, the hopping exponential
 //     read through L1 (it is shared by all chains and stays cached), the diagonal e^{+-V} factors fused as k / row /
 //     column scales.
+// One flavor block (the register-patch path below), where an accept's ~2200 cycles went according to the ncu source page
+// (profiles/r2i_slice_steps_source_regions.txt, before the last three changes): evaluation + extraction 42 % of the kernel's
+// samples, the barrier 17 %, the shared-memory loads behind it 22 %, the two wrap products 17 %.  In the build: uniform switch for the
+// patch column / row, half evaluation, padded 128-bit exchange, rank-1 update rotated into the next iteration (cfg 2: 9493 -> 10 912
+// sweeps/s).  Measured and not kept: a cheaper trace path for warp 0 (one vote in front of the statistics / trace stores): 10 922 vs
+// 10 912 -- warp 0 is not what the barrier waits for.
 // The host state machine (capi.cu) replaces each run of "sweep_spatial + plain wrap" by one launch and keeps the
 // separate kernels for the stabilisation steps.  Decisions are identical to the generic path and to the reference
 // for the same uniforms (tests/test_gpu_parity.py covers both via dqmc_desc.update_variant).
